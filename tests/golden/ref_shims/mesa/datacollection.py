@@ -1,0 +1,3 @@
+class DataCollector:
+    def __init__(self, *a, **k):
+        pass
