@@ -1,0 +1,323 @@
+"""ctypes binding of libabm_b200.so and the `Simulation` object that owns one rank's agent store.
+
+PyTorch is used only to own device buffers (and, multi-GPU, to rendezvous); every computation of the
+agent step happens in the CUDA library.  There is no CPU fallback: constructing a `Simulation` without
+the built library or without a CUDA device raises.
+
+Role in the reference: this is what `Country` + `EpidemicScheduler` are on the host
+(/root/reference/src/covid19_abm/base_model.py:20-441, 444-634): the vectors, the clock, `step()`.
+"""
+import ctypes as ct
+import os
+from datetime import timedelta
+
+import numpy as np
+
+from . import constants as C
+from . import layout, tables as tables_mod
+from .spec import ModelSpec, Population
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libabm_b200.so')
+
+COUNTER_NAMES = ['current_contagious_count', 'infected_count', 'hospitalized_count', 'critical_count', 'died_count',
+                 'recovered_count', 'current_exposed_cases', 'current_contagious_cases', 'current_hospitalized_cases',
+                 'current_critical_cases', 'asymptomatic_count', 'symptomatic_count']
+LOG_STRIDE = 16
+LOG_TICK = 12
+
+
+class AbmConfig(ct.Structure):
+    _fields_ = [('n_slots', ct.c_int64), ('n_tiles', ct.c_int64), ('agent_id_base', ct.c_int64),
+                ('n_districts', ct.c_int32), ('n_status', ct.c_int32), ('n_pools', ct.c_int32), ('hw_rows', ct.c_int32),
+                ('n_move_classes', ct.c_int32), ('n_big_households', ct.c_int32), ('step_ticks', ct.c_int32),
+                ('start_minute_of_day', ct.c_int32), ('start_weekday', ct.c_int32), ('mild_active', ct.c_int32),
+                ('max_log_rows', ct.c_int32), ('device', ct.c_int32), ('seed', ct.c_uint64),
+                ('symptomatic_rate', ct.c_double), ('critical_fatality_rate', ct.c_double), ('stream', ct.c_void_p),
+                ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
+
+
+class AbmTables(ct.Structure):
+    _fields_ = [(n, ct.c_void_p) for n in
+                ('rfx', 'qfx', 'W', 'pool_hw', 'od_thr', 'stay_par', 'dwell', 'znorm', 'p_hosp', 'p_crit', 'p_hfat',
+                 'severe_risk', 'move_thr', 'district_start', 'tile_base', 'tile_home', 'big_start')]
+
+
+class AbmAgentPtrs(ct.Structure):
+    _fields_ = [(n, ct.c_void_p) for n in
+                ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
+                 'move_class', 'econ_pool')]
+
+
+EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
+           'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
+           'abm_kernel_time', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
+           'abm_version']
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} not found: build it with `python __graft_entry__.py build` '
+                           '(the agent step has no CPU fallback)')
+    lib = ct.CDLL(path)
+    for name in EXPORTS:
+        getattr(lib, name)
+    vp = ct.c_void_p
+    lib.abm_create.argtypes = [ct.POINTER(AbmConfig), ct.POINTER(vp)]
+    lib.abm_set_tables.argtypes = [vp, ct.POINTER(AbmTables)]
+    lib.abm_bind_agents.argtypes = [vp, ct.POINTER(AbmAgentPtrs)]
+    lib.abm_refresh.argtypes = [vp, vp, ct.c_int32]
+    lib.abm_seed.argtypes = [vp, vp, vp, ct.c_int64]
+    lib.abm_step.argtypes = [vp, ct.c_int32]
+    lib.abm_flush.argtypes = [vp]
+    lib.abm_read_log.argtypes = [vp, vp, ct.c_int32, ct.POINTER(ct.c_int32)]
+    lib.abm_counters.argtypes = [vp, vp]
+    lib.abm_district_symptomatic.argtypes = [vp, vp, vp]
+    lib.abm_debug_tables.argtypes = [vp, vp, vp, vp]
+    lib.abm_set_profiling.argtypes = [vp, ct.c_int32]
+    lib.abm_kernel_time.argtypes = [vp, ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
+    lib.abm_current_step.argtypes = [vp]
+    lib.abm_current_step.restype = ct.c_int64
+    lib.abm_launch_count.argtypes = [vp]
+    lib.abm_launch_count.restype = ct.c_int64
+    lib.abm_sync.argtypes = [vp]
+    lib.abm_last_error.argtypes = [vp]
+    lib.abm_last_error.restype = ct.c_char_p
+    lib.abm_destroy.argtypes = [vp]
+    lib.abm_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+class Simulation:
+    """One rank's share of the population on one GPU.
+
+    pop            canonical-order agents of this rank (household-aligned shard)
+    agent_id_base  canonical id of pop's first agent (Philox key; makes results independent of sharding)
+    district_start global canonical id of the first agent of every home district [D + 1]
+    """
+
+    def __init__(self, spec: ModelSpec, pop: Population, seed=0, device=0, tables=None, max_days=400,
+                 agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('abm_b200 needs a CUDA device (no CPU fallback)')
+        self.torch = torch
+        self.lib = load_library()
+        self.spec, self.pop = spec, pop
+        self.tab = tables if tables is not None else tables_mod.build_tables(spec)
+        self.device = torch.device('cuda', device)
+        self.sm = layout.build_slot_map(pop.household, agent_id_base)
+        sm = self.sm
+        D = spec.n_districts
+        if district_start is None:
+            district_start = np.searchsorted(pop.district, np.arange(D + 1)).astype(np.int64) + agent_id_base
+        self.district_start = np.ascontiguousarray(district_start, dtype=np.int64)
+        self.move_class, self.move_thr, _ = tables_mod.move_classes(pop, spec.mild_symptom_move_prob)
+        flags, aux = layout.pack_flags(pop, sm)
+        n_slots = sm.n_slots
+
+        def dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+        def slots_from_agents(values, fill, dtype):
+            out = np.full(n_slots, fill, dtype=dtype)
+            out[sm.slot_of] = values
+            return out
+
+        never = np.int32(C.T_NEVER)
+        self.buf = dict(
+            flags=dev(flags.view(np.int32)), aux=dev(aux.view(np.int32)),
+            t_infected=dev(np.full(n_slots, never, np.int32)), t_contagious=dev(np.full(n_slots, never, np.int32)),
+            t_onset=dev(np.full(n_slots, never, np.int32)), t_recovered=dev(np.full(n_slots, never, np.int32)),
+            t_return=dev(np.full(n_slots, never, np.int32)), inf_at=dev(np.zeros(n_slots, np.int32)),
+            move_class=dev(slots_from_agents(self.move_class, 0, np.uint16).view(np.int16)),
+        )
+        if pop.econ_pool is not None:
+            self.buf['econ_pool'] = dev(slots_from_agents(pop.econ_pool.astype(np.int32), 0, np.int32))
+        tile_home = pop.district[np.clip(sm.tile_base[:-1] - agent_id_base, 0, pop.n - 1)].astype(np.uint16)
+
+        cfg = AbmConfig()
+        cfg.n_slots, cfg.n_tiles, cfg.agent_id_base = n_slots, sm.n_tiles, agent_id_base
+        cfg.n_districts, cfg.n_status, cfg.n_pools, cfg.hw_rows = D, spec.n_status, spec.n_pools, self.tab['hw_rows']
+        cfg.n_move_classes, cfg.n_big_households = self.move_thr.shape[0], sm.big_size.shape[0]
+        cfg.step_ticks = self.tab['step_ticks']
+        cfg.start_minute_of_day, cfg.start_weekday = self.tab['start_minute_of_day'], self.tab['start_weekday']
+        cfg.mild_active = int(self.tab['mild_active'])
+        self.steps_per_day = (24 * 60) // cfg.step_ticks
+        cfg.max_log_rows = int(max_days) + 2
+        cfg.device = device
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.symptomatic_rate, cfg.critical_fatality_rate = self.tab['symptomatic_rate'], self.tab['critical_fatality_rate']
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        cfg.stream = self.stream.cuda_stream
+        cfg.world_size, cfg.rank = world_size, rank
+        self._uid = None
+        if world_size > 1:
+            self._uid = (ct.c_char * 128).from_buffer_copy(bytes(nccl_unique_id))
+            cfg.nccl_unique_id = ct.cast(self._uid, ct.c_void_p)
+        self.h = ct.c_void_p()
+        self._check(self.lib.abm_create(ct.byref(cfg), ct.byref(self.h)))
+        self.cfg = cfg
+
+        t = self.tab
+        keep = dict(
+            rfx=t['rfx'], qfx=t['qfx'], W=t['W'], pool_hw=t['pool_hw'], od_thr=t['od_thr'], stay_par=t['stay_par'],
+            dwell=t['dwell'], znorm=t['znorm'], p_hosp=t['p_hosp'], p_crit=t['p_crit'], p_hfat=t['p_hfat'],
+            severe_risk=t['severe_risk'], move_thr=self.move_thr, district_start=self.district_start,
+            tile_base=np.ascontiguousarray(sm.tile_base), tile_home=np.ascontiguousarray(tile_home),
+            big_start=np.ascontiguousarray(sm.big_start))
+        at = AbmTables()
+        for name, arr in keep.items():
+            setattr(at, name, _ptr(arr))
+        self._check(self.lib.abm_set_tables(self.h, ct.byref(at)))
+        ap = AbmAgentPtrs()
+        for name in ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
+                     'move_class'):
+            setattr(ap, name, self.buf[name].data_ptr())
+        ap.econ_pool = self.buf['econ_pool'].data_ptr() if 'econ_pool' in self.buf else None
+        self._check(self.lib.abm_bind_agents(self.h, ct.byref(ap)))
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.abm_last_error(self.h) if self.h else b'create failed'
+            raise RuntimeError(f'abm_b200 error {rc}: {msg.decode()}')
+
+    @property
+    def n_agents(self):
+        return self.pop.n
+
+    @property
+    def step_index(self):
+        return int(self.lib.abm_current_step(self.h))
+
+    @property
+    def real_time(self):
+        return self.spec.start_datetime + timedelta(minutes=self.step_index * self.cfg.step_ticks)
+
+    # ------------------------------------------------------------------ the path
+    def seed_infections(self, agent_ids):
+        """Country.set_epidemic_status(ids) at the current time (base_model.py:796)."""
+        ids = np.ascontiguousarray(agent_ids, dtype=np.int64)
+        local = ids - self.sm.agent_id_base
+        slots = np.ascontiguousarray(self.sm.slot_of[local])
+        self._check(self.lib.abm_seed(self.h, _ptr(slots), _ptr(ids), ids.shape[0]))
+
+    def step(self, n_substeps=1):
+        """n x EpidemicScheduler.step() (base_model.py:33-179); asynchronous."""
+        self._check(self.lib.abm_step(self.h, int(n_substeps)))
+
+    def flush(self):
+        self._check(self.lib.abm_flush(self.h))
+
+    def sync(self):
+        self._check(self.lib.abm_sync(self.h))
+
+    def refresh(self):
+        """Re-encode the vectors scenario hooks mutate on the host (district_mover, movement probabilities,
+        economic_activity_location_ids; base_model.py:642-731) and push them to the device."""
+        torch = self.torch
+        self.flush()
+        self.sync()
+        flags = self.buf['flags'].cpu().numpy().view(np.uint32)
+        layout.update_static_fields(flags, self.pop, self.sm)
+        self.buf['flags'].copy_(torch.from_numpy(flags.view(np.int32)))
+        self.move_class, self.move_thr, _ = tables_mod.move_classes(self.pop, self.spec.mild_symptom_move_prob)
+        mc = np.zeros(self.sm.n_slots, dtype=np.uint16)
+        mc[self.sm.slot_of] = self.move_class
+        self.buf['move_class'].copy_(torch.from_numpy(mc.view(np.int16)))
+        if self.pop.econ_pool is not None and 'econ_pool' in self.buf:
+            ep = np.zeros(self.sm.n_slots, dtype=np.int32)
+            ep[self.sm.slot_of] = self.pop.econ_pool
+            self.buf['econ_pool'].copy_(torch.from_numpy(ep))
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.abm_refresh(self.h, _ptr(self.move_thr), self.move_thr.shape[0]))
+
+    # ------------------------------------------------------------------ read-back
+    def read_log(self):
+        """Rows of Country.log_model_output produced so far: list of dicts (this rank's agents)."""
+        rows = np.zeros((self.cfg.max_log_rows, LOG_STRIDE), dtype=np.int64)
+        n = ct.c_int32()
+        self._check(self.lib.abm_read_log(self.h, _ptr(rows), self.cfg.max_log_rows, ct.byref(n)))
+        return rows[:n.value]
+
+    def log_dicts(self, rows=None):
+        rows = self.read_log() if rows is None else rows
+        out = []
+        for r in rows:
+            d = {name: int(r[i]) for i, name in enumerate(COUNTER_NAMES)}
+            d['tick'] = int(r[LOG_TICK])
+            d['date'] = (self.spec.start_datetime + timedelta(minutes=int(r[LOG_TICK]))).isoformat()
+            out.append(d)
+        return out
+
+    def counters(self):
+        out = np.zeros(12, dtype=np.int64)
+        self._check(self.lib.abm_counters(self.h, _ptr(out)))
+        return {name: int(out[i]) for i, name in enumerate(COUNTER_NAMES)}
+
+    def district_symptomatic(self):
+        D = self.spec.n_districts
+        sym, pop = np.zeros(D, dtype=np.int64), np.zeros(D, dtype=np.int64)
+        self._check(self.lib.abm_district_symptomatic(self.h, _ptr(sym), _ptr(pop)))
+        return sym, pop
+
+    def debug_tables(self):
+        pa = self.spec.n_pools * self.spec.n_status
+        r, n, t = np.zeros(pa, np.uint64), np.zeros(pa, np.uint64), np.zeros(pa, np.uint32)
+        self._check(self.lib.abm_debug_tables(self.h, _ptr(r), _ptr(n), _ptr(t)))
+        shp = (self.spec.n_pools, self.spec.n_status)
+        return r.reshape(shp), n.reshape(shp), t.reshape(shp)
+
+    def download(self):
+        """Device SoA -> host numpy (slot order); applies pending infection draws first."""
+        self.flush()
+        self.sync()
+        out = {}
+        for k, v in self.buf.items():
+            a = v.cpu().numpy()
+            if k in ('flags', 'aux', 'inf_at'):
+                a = a.view(np.uint32)
+            elif k == 'move_class':
+                a = a.view(np.uint16)
+            out[k] = a
+        return out
+
+    def state(self):
+        """Reference-style vectors over this rank's agents (see layout.unpack_state)."""
+        return layout.unpack_state(self.download(), self.pop, self.sm, self.spec.n_districts)
+
+    def set_profiling(self, on):
+        self._check(self.lib.abm_set_profiling(self.h, int(bool(on))))
+
+    def kernel_time(self):
+        ms, n = ct.c_double(), ct.c_int64()
+        self._check(self.lib.abm_kernel_time(self.h, ct.byref(ms), ct.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self):
+        return int(self.lib.abm_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.abm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -129,23 +129,31 @@ def lockdown_rates(n_districts, seed=0):
     return np.random.default_rng(seed + 1299709).uniform(0.4, 1.0, n_districts)
 
 
-def pick_seeds(pop: Population, spec: ModelSpec, infect_num=None, seed=0, n_seed_districts=6):
+def seed_case_counts(pop: Population, spec: ModelSpec, seed=0, n_seed_districts=6):
+    """Line-list stand-in: {district id: reported cases} over the most populous districts."""
+    rng = np.random.default_rng([seed, 49979687])
+    D = spec.n_districts
+    order = np.argsort(-np.bincount(pop.district, minlength=D), kind='stable')
+    seed_districts = order[:min(n_seed_districts, D)]
+    cases = rng.integers(5, 60, seed_districts.shape[0])
+    return {int(d): int(c) for d, c in zip(seed_districts, cases)}
+
+
+def pick_seeds(pop: Population, spec: ModelSpec, infect_num=None, seed=0, cases=None):
     """Seed ids as `Country.load_agents` draws them (base_model.py:780-796): per line-list district
     int(p * infect_num) + 1 agents with age strictly in (20, 60), without replacement."""
-    rng = np.random.default_rng([seed, 49979687])
+    rng = np.random.default_rng([seed, 86028121])
     n = pop.n
     if infect_num is None:
         infect_num = max(1, int(round(0.00015 * n)))
-    D = spec.n_districts
-    order = np.argsort(-np.bincount(pop.district, minlength=D))
-    seed_districts = order[:min(n_seed_districts, D)]
-    cases = rng.integers(5, 60, seed_districts.shape[0]).astype(np.float64)
-    prob = cases / cases.sum()
-    bounds = np.searchsorted(pop.district, np.arange(D + 1))
+    if cases is None:
+        cases = seed_case_counts(pop, spec, seed)
+    total = float(sum(cases.values()))
+    bounds = np.searchsorted(pop.district, np.arange(spec.n_districts + 1))
     out = []
-    for d, p in zip(seed_districts, prob):
+    for d, c in cases.items():
         lo, hi = bounds[d], bounds[d + 1]
         cand = lo + np.nonzero((pop.age[lo:hi] > 20) & (pop.age[lo:hi] < 60))[0]
-        k = min(int(p * infect_num) + 1, cand.shape[0])
+        k = min(int(c / total * infect_num) + 1, cand.shape[0])
         out.append(rng.choice(cand, size=k, replace=False))
     return np.sort(np.concatenate(out)).astype(np.int64)

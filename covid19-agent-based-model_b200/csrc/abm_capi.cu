@@ -1,0 +1,463 @@
+// abm_capi.cu -- host side of libabm_b200.so: the C ABI declared in include/abm_b200.h.
+//
+// Replaces, for the hot path only, what Country / EpidemicScheduler do on the host in the reference
+// (/root/reference/src/covid19_abm/base_model.py:20-441, 838-1106): owns the constant tables, the
+// district x status accumulators, the day log, the sub-step clock, and launches the kernels of
+// abm_kernels.cuh on one CUDA stream.  Multi-GPU: one handle per rank, the accumulators are summed over
+// ranks with one ncclAllReduce per sub-step (NCCL is loaded with dlopen so a single-GPU build has no
+// link-time dependency on it).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "abm_kernels.cuh"
+
+using namespace abm;
+
+namespace {
+
+typedef ncclResult_t (*nccl_init_rank_fn)(ncclComm_t*, int, ncclUniqueId, int);
+typedef ncclResult_t (*nccl_allreduce_fn)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*nccl_destroy_fn)(ncclComm_t);
+typedef const char* (*nccl_errstr_fn)(ncclResult_t);
+
+struct SeedEvent { int32_t tick; int64_t n; };
+
+}  // namespace
+
+struct abm_handle {
+    abm_config cfg{};
+    DevTables T{};
+    DevAgents G{};
+    bool have_tables = false, have_agents = false;
+    std::vector<void*> owned;           // device allocations to free
+    unsigned long long* acc = nullptr;  // [2][P][A]
+    unsigned long long* acc_snapshot = nullptr;
+    uint32_t* thr_out = nullptr;        // [P][A]
+    unsigned long long* hbig[2] = {nullptr, nullptr};
+    unsigned long long* cum = nullptr;  // [N_TALLY]
+    long long* daylog = nullptr;        // [max_log_rows + 1][ABM_LOG_STRIDE]; last row is scratch
+    uint32_t* move_thr = nullptr;
+    int32_t n_move_classes = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t k = 0;                      // next sub-step to execute
+    bool pending_infect = false;        // I(k-1) not applied yet
+    int32_t n_log_rows = 0;
+    std::vector<SeedEvent> seeds;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    double prof_ms = 0.0;
+    int64_t prof_launches = 0;
+    int64_t launches = 0;
+    // NCCL
+    void* nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    nccl_allreduce_fn nccl_allreduce = nullptr;
+    nccl_destroy_fn nccl_destroy = nullptr;
+    nccl_errstr_fn nccl_errstr = nullptr;
+    std::string err;
+};
+
+namespace {
+
+int fail(abm_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail(h, ABM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename Tp>
+int upload(abm_handle* h, const Tp* host, size_t count, const Tp** dev_out) {
+    Tp* d = nullptr;
+    if (count == 0) count = 1;
+    CUDA_TRY(h, cudaMalloc(&d, count * sizeof(Tp)));
+    h->owned.push_back(d);
+    if (host) CUDA_TRY(h, cudaMemcpyAsync(d, host, count * sizeof(Tp), cudaMemcpyHostToDevice, h->stream));
+    else CUDA_TRY(h, cudaMemsetAsync(d, 0, count * sizeof(Tp), h->stream));
+    *dev_out = d;
+    return ABM_OK;
+}
+
+template <typename Tp>
+int alloc_zero(abm_handle* h, size_t count, Tp** dev_out) {
+    const Tp* p = nullptr;
+    int rc = upload<Tp>(h, nullptr, count, &p);
+    *dev_out = const_cast<Tp*>(p);
+    return rc;
+}
+
+int32_t hour_of(const abm_config& c, int64_t tick) { return (int32_t)(((c.start_minute_of_day + tick) / 60) % 24); }
+int32_t weekday_of(const abm_config& c, int64_t tick) {
+    return (int32_t)((c.start_weekday + (c.start_minute_of_day + tick) / 1440) % 7);
+}
+
+int launch_main(abm_handle* h, const StepArgs& s, long long* log_row) {
+    DevWork w{};
+    w.acc = h->acc;
+    w.thr_out = h->thr_out;
+    w.hbig_write = h->hbig[s.k & 1];
+    w.hbig_read = h->hbig[(s.k + 1) & 1];
+    w.cum = h->cum;
+    w.log_row = log_row;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        if (h->prof_used == h->prof_events.size()) {
+            CUDA_TRY(h, cudaEventCreate(&e0));
+            CUDA_TRY(h, cudaEventCreate(&e1));
+            h->prof_events.emplace_back(e0, e1);
+        }
+        e0 = h->prof_events[h->prof_used].first;
+        e1 = h->prof_events[h->prof_used].second;
+        h->prof_used++;
+        CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+    }
+    abm_substep_kernel<<<(unsigned)h->cfg.n_tiles, THREADS, 0, h->stream>>>(h->T, h->G, w, s);
+    if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return ABM_OK;
+}
+
+int collect_profile(abm_handle* h) {
+    if (h->prof_used == 0) return ABM_OK;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+        h->prof_ms += ms;
+    }
+    h->prof_launches += (int64_t)h->prof_used;
+    h->prof_used = 0;
+    return ABM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int abm_version(void) { return 100; }
+
+const char* abm_last_error(abm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int abm_create(const abm_config* cfg, abm_handle** out) {
+    if (!cfg || !out) return ABM_ERR_ARG;
+    *out = nullptr;
+    abm_handle* h = new abm_handle();
+    *out = h;   // returned even on failure so the caller can read the message, then abm_destroy
+    h->cfg = *cfg;
+    if (cfg->n_slots <= 0 || cfg->n_slots != cfg->n_tiles * ABM_TILE) return fail(h, ABM_ERR_ARG, "n_slots must be n_tiles * %d", ABM_TILE);
+    if (cfg->n_status < 1 || cfg->n_status > ABM_MAX_STATUS) return fail(h, ABM_ERR_ARG, "n_status must be 1..%d", ABM_MAX_STATUS);
+    if (cfg->n_districts < 1 || cfg->n_districts > 65535 || cfg->n_pools < cfg->n_districts) return fail(h, ABM_ERR_ARG, "bad district / pool count");
+    if (cfg->hw_rows != 1 && cfg->hw_rows != cfg->n_districts) return fail(h, ABM_ERR_ARG, "hw_rows must be 1 or n_districts");
+    if (cfg->step_ticks <= 0 || cfg->max_log_rows < 1) return fail(h, ABM_ERR_ARG, "bad step_ticks / max_log_rows");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, ABM_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    CUDA_TRY(h, cudaSetDevice(cfg->device));
+    if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
+    else { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
+    int rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc))) return rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc_snapshot))) return rc;
+    if ((rc = alloc_zero(h, pa, &h->thr_out))) return rc;
+    if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[0]))) return rc;
+    if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[1]))) return rc;
+    if ((rc = alloc_zero(h, (size_t)N_TALLY, &h->cum))) return rc;
+    if ((rc = alloc_zero(h, (size_t)(cfg->max_log_rows + 1) * ABM_LOG_STRIDE, &h->daylog))) return rc;
+    if (cfg->world_size > 1) {
+        if (!cfg->nccl_unique_id) return fail(h, ABM_ERR_ARG, "world_size > 1 needs an ncclUniqueId");
+        h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h->nccl_lib) return fail(h, ABM_ERR_NCCL, "dlopen libnccl.so.2: %s", dlerror());
+        nccl_init_rank_fn init = (nccl_init_rank_fn)dlsym(h->nccl_lib, "ncclCommInitRank");
+        h->nccl_allreduce = (nccl_allreduce_fn)dlsym(h->nccl_lib, "ncclAllReduce");
+        h->nccl_destroy = (nccl_destroy_fn)dlsym(h->nccl_lib, "ncclCommDestroy");
+        h->nccl_errstr = (nccl_errstr_fn)dlsym(h->nccl_lib, "ncclGetErrorString");
+        if (!init || !h->nccl_allreduce || !h->nccl_destroy) return fail(h, ABM_ERR_NCCL, "NCCL symbols missing");
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_unique_id, sizeof id);
+        ncclResult_t r = init(&h->comm, cfg->world_size, id, cfg->rank);
+        if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclCommInitRank: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ABM_OK;
+}
+
+int abm_set_tables(abm_handle* h, const abm_tables* t) {
+    if (!h || !t) return ABM_ERR_ARG;
+    const abm_config& c = h->cfg;
+    const size_t D = c.n_districts, A = c.n_status, P = c.n_pools;
+    DevTables& T = h->T;
+    int rc;
+    if ((rc = upload(h, t->rfx, 2 * 128, &T.rfx))) return rc;
+    if ((rc = upload(h, t->qfx, (size_t)c.hw_rows * 2 * 128, &T.qfx))) return rc;
+    if ((rc = upload(h, t->W, A * A, &T.W))) return rc;
+    if ((rc = upload(h, t->pool_hw, P, &T.pool_hw))) return rc;
+    if ((rc = upload(h, t->od_thr, 7 * D * D, &T.od_thr))) return rc;
+    if ((rc = upload(h, t->stay_par, 7 * D * D * 3, &T.stay_par))) return rc;
+    if ((rc = upload(h, t->dwell, (size_t)4 * 2 * (ABM_QN + 1), &T.dwell))) return rc;
+    if ((rc = upload(h, t->znorm, (size_t)2 * (ABM_QN + 1), &T.znorm))) return rc;
+    if ((rc = upload(h, t->p_hosp, 128, &T.p_hosp))) return rc;
+    if ((rc = upload(h, t->p_crit, 128, &T.p_crit))) return rc;
+    if ((rc = upload(h, t->p_hfat, 128, &T.p_hfat))) return rc;
+    if ((rc = upload(h, t->severe_risk, D, &T.severe_risk))) return rc;
+    const uint32_t* mt = nullptr;
+    if ((rc = upload(h, t->move_thr, (size_t)c.n_move_classes * 4, &mt))) return rc;
+    T.move_thr = mt;
+    h->n_move_classes = c.n_move_classes;
+    if ((rc = upload(h, t->district_start, D + 1, &T.district_start))) return rc;
+    if ((rc = upload(h, t->tile_base, (size_t)c.n_tiles + 1, &T.tile_base))) return rc;
+    if ((rc = upload(h, t->tile_home, (size_t)c.n_tiles, &T.tile_home))) return rc;
+    if ((rc = upload(h, t->big_start, (size_t)c.n_big_households + 1, &T.big_start))) return rc;
+    T.D = c.n_districts; T.A = c.n_status; T.P = c.n_pools; T.hw_rows = c.hw_rows; T.n_big = c.n_big_households;
+    T.step_ticks = c.step_ticks; T.mild_active = c.mild_active;
+    T.seed_lo = (uint32_t)c.seed; T.seed_hi = (uint32_t)(c.seed >> 32);
+    T.symptomatic_rate = c.symptomatic_rate; T.critical_fatality_rate = c.critical_fatality_rate;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // host staging buffers may be released by the caller
+    h->have_tables = true;
+    return ABM_OK;
+}
+
+int abm_bind_agents(abm_handle* h, const abm_agent_ptrs* dev) {
+    if (!h || !dev) return ABM_ERR_ARG;
+    if (!dev->flags || !dev->aux || !dev->t_infected || !dev->t_contagious || !dev->t_onset || !dev->t_recovered ||
+        !dev->t_return || !dev->inf_at || !dev->move_class)
+        return fail(h, ABM_ERR_ARG, "null agent buffer");
+    if (((uintptr_t)dev->flags | (uintptr_t)dev->aux) & 15) return fail(h, ABM_ERR_ARG, "flags/aux must be 16-byte aligned");
+    DevAgents& G = h->G;
+    G.flags = dev->flags; G.aux = dev->aux; G.t_infected = dev->t_infected; G.t_contagious = dev->t_contagious;
+    G.t_onset = dev->t_onset; G.t_recovered = dev->t_recovered; G.t_return = dev->t_return; G.inf_at = dev->inf_at;
+    G.move_class = dev->move_class; G.econ_pool = dev->econ_pool;
+    h->have_agents = true;
+    return ABM_OK;
+}
+
+int abm_refresh(abm_handle* h, const uint32_t* move_thr, int32_t n_move_classes) {
+    if (!h) return ABM_ERR_ARG;
+    if (move_thr) {
+        if (n_move_classes < 1) return fail(h, ABM_ERR_ARG, "n_move_classes < 1");
+        const uint32_t* mt = nullptr;
+        int rc = upload(h, move_thr, (size_t)n_move_classes * 4, &mt);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->T.move_thr = mt;
+        h->n_move_classes = n_move_classes;
+    }
+    return ABM_OK;
+}
+
+int abm_seed(abm_handle* h, const int64_t* slots, const int64_t* ids, int64_t n) {
+    if (!h || (n > 0 && (!slots || !ids))) return ABM_ERR_ARG;
+    if (!h->have_tables || !h->have_agents) return fail(h, ABM_ERR_STATE, "tables / agents not set");
+    if (n <= 0) return ABM_OK;
+    int rc = abm_flush(h);
+    if (rc) return rc;
+    int64_t *d_slots = nullptr, *d_ids = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_slots, n * sizeof(int64_t)));
+    CUDA_TRY(h, cudaMalloc(&d_ids, n * sizeof(int64_t)));
+    CUDA_TRY(h, cudaMemcpyAsync(d_slots, slots, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_ids, ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    const int32_t now = (int32_t)(h->k * h->cfg.step_ticks);
+    abm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->T, h->G, h->cum, d_slots, d_ids, n, (int32_t)h->k, now);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_slots);
+    cudaFree(d_ids);
+    h->seeds.push_back(SeedEvent{now, n});
+    h->launches++;
+    return ABM_OK;
+}
+
+int abm_step(abm_handle* h, int32_t n_substeps) {
+    if (!h || n_substeps < 0) return ABM_ERR_ARG;
+    if (!h->have_tables || !h->have_agents) return fail(h, ABM_ERR_STATE, "tables / agents not set");
+    const abm_config& c = h->cfg;
+    const int pa = c.n_pools * c.n_status;
+    for (int32_t i = 0; i < n_substeps; ++i) {
+        if (h->k >= 0xFFF0) return fail(h, ABM_ERR_STATE, "sub-step index exceeds the 16-bit event field");
+        const int64_t tick = h->k * c.step_ticks;
+        if (tick + 2 * c.step_ticks >= 0x7FFFFFFF) return fail(h, ABM_ERR_STATE, "tick overflow");
+        const int32_t hour = hour_of(c, tick), wd = weekday_of(c, tick);
+        StepArgs s{};
+        s.k = (int32_t)h->k; s.now = (int32_t)tick; s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks; s.weekday = wd;
+        s.mode = M_STEP | (h->pending_infect ? M_INFECT : 0u);
+        if (hour == 8) s.mode |= M_GO_OUT;            // params.py:131,135
+        if (hour == 16) s.mode |= M_GO_HOME;          // params.py:132,136
+        if (wd <= 4) s.mode |= M_WEEKDAY;             // base_model.py:309
+        const bool log = hour == 8;                   // base_model.py:1083
+        long long* row = h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE;   // scratch row
+        if (log) {
+            if (h->n_log_rows >= c.max_log_rows) return fail(h, ABM_ERR_STATE, "day log full (%d rows)", c.max_log_rows);
+            s.mode |= M_LOG;
+            row = h->daylog + (size_t)h->n_log_rows * ABM_LOG_STRIDE;
+        }
+        int rc = launch_main(h, s, row);
+        if (rc) return rc;
+        if (h->comm) {
+            ncclResult_t r = h->nccl_allreduce(h->acc, h->acc, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
+            if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
+        }
+        TableArgs ta{};
+        ta.write_log = log ? 1 : 0;
+        ta.tick = (int32_t)tick;
+        ta.seeds_before_now = 0;
+        for (const SeedEvent& e : h->seeds)
+            if (e.tick < tick) ta.seeds_before_now += e.n;
+        const int nthreads = pa > c.n_big_households ? pa : c.n_big_households;
+        abm_hazard_table_kernel<<<(nthreads + 127) / 128, 128, 0, h->stream>>>(h->T, h->acc, h->acc_snapshot, h->thr_out,
+                                                                              h->hbig[(s.k + 1) & 1], h->cum, row, ta);
+        abm_clear_tables_kernel<<<(2 * pa + 127) / 128, 128, 0, h->stream>>>(h->acc, h->acc_snapshot, 2 * pa);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 2;
+        if (log) h->n_log_rows++;
+        h->k++;
+        h->pending_infect = true;
+    }
+    return ABM_OK;
+}
+
+int abm_flush(abm_handle* h) {
+    if (!h) return ABM_ERR_ARG;
+    if (!h->pending_infect) return ABM_OK;
+    const abm_config& c = h->cfg;
+    StepArgs s{};
+    s.k = (int32_t)h->k; s.now = (int32_t)(h->k * c.step_ticks); s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks;
+    s.weekday = weekday_of(c, s.now);
+    s.mode = M_INFECT;
+    int rc = launch_main(h, s, h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE);
+    if (rc) return rc;
+    h->pending_infect = false;
+    return ABM_OK;
+}
+
+int abm_sync(abm_handle* h) {
+    if (!h) return ABM_ERR_ARG;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ABM_OK;
+}
+
+int abm_read_log(abm_handle* h, int64_t* out, int32_t max_rows, int32_t* n_rows) {
+    if (!h || !out || !n_rows) return ABM_ERR_ARG;
+    const int32_t n = h->n_log_rows < max_rows ? h->n_log_rows : max_rows;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->daylog, (size_t)n * ABM_LOG_STRIDE * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *n_rows = n;
+    return ABM_OK;
+}
+
+int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
+    if (!h || !out) return ABM_ERR_ARG;
+    int rc = abm_flush(h);
+    if (rc) return rc;
+    unsigned long long* d4 = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d4, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(d4, 0, 4 * sizeof(unsigned long long), h->stream));
+    const int64_t n = h->cfg.n_slots;
+    abm_count_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->G, n, d4);
+    unsigned long long cur[4], cum[N_TALLY];
+    CUDA_TRY(h, cudaMemcpyAsync(cur, d4, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(cum, h->cum, sizeof cum, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d4);
+    h->launches++;
+    // NOTE: cumulative date counters cover events whose date precedes the LAST executed sub-step's clock;
+    // the day log (abm_read_log) holds the exact log_model_output values.
+    const int64_t tick = h->k * h->cfg.step_ticks;
+    int64_t seeded = 0;
+    for (const SeedEvent& e : h->seeds)
+        if (e.tick < tick) seeded += e.n;
+    out[ABM_C_CURRENT_CONTAGIOUS_COUNT] = (int64_t)cum[CUM_CONTAGIOUS];
+    out[ABM_C_INFECTED_COUNT] = (int64_t)cum[CUM_INFECTED] + seeded;
+    out[ABM_C_HOSPITALIZED_COUNT] = (int64_t)cum[CUM_HOSPITALIZED];
+    out[ABM_C_CRITICAL_COUNT] = (int64_t)cum[CUM_CRITICAL];
+    out[ABM_C_DIED_COUNT] = (int64_t)cum[CUM_DIED];
+    out[ABM_C_RECOVERED_COUNT] = (int64_t)cum[CUM_RECOVERED];
+    out[ABM_C_CURRENT_EXPOSED_CASES] = (int64_t)cur[0];
+    out[ABM_C_CURRENT_CONTAGIOUS_CASES] = (int64_t)cur[1];
+    out[ABM_C_CURRENT_HOSPITALIZED_CASES] = (int64_t)cur[2];
+    out[ABM_C_CURRENT_CRITICAL_CASES] = (int64_t)cur[3];
+    out[ABM_C_ASYMPTOMATIC_COUNT] = (int64_t)cum[CUM_ASYM];
+    out[ABM_C_SYMPTOMATIC_COUNT] = (int64_t)cum[CUM_SYM];
+    return ABM_OK;
+}
+
+int abm_district_symptomatic(abm_handle* h, int64_t* sym, int64_t* pop) {
+    if (!h || !sym || !pop) return ABM_ERR_ARG;
+    int rc = abm_flush(h);
+    if (rc) return rc;
+    const int D = h->cfg.n_districts;
+    unsigned long long* d = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d, 2 * D * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(d, 0, 2 * D * sizeof(unsigned long long), h->stream));
+    const int64_t n = h->cfg.n_slots;
+    abm_district_sym_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->T, h->G, n, d, d + D);
+    CUDA_TRY(h, cudaMemcpyAsync(sym, d, D * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(pop, d + D, D * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    h->launches++;
+    return ABM_OK;
+}
+
+int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* thr) {
+    if (!h) return ABM_ERR_ARG;
+    const size_t pa = (size_t)h->cfg.n_pools * h->cfg.n_status;
+    if (rsum) CUDA_TRY(h, cudaMemcpyAsync(rsum, h->acc_snapshot, pa * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (ncnt) CUDA_TRY(h, cudaMemcpyAsync(ncnt, h->acc_snapshot + pa, pa * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (thr) CUDA_TRY(h, cudaMemcpyAsync(thr, h->thr_out, pa * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ABM_OK;
+}
+
+int abm_set_profiling(abm_handle* h, int32_t on) {
+    if (!h) return ABM_ERR_ARG;
+    int rc = collect_profile(h);
+    if (rc) return rc;
+    h->profiling = on != 0;
+    h->prof_ms = 0.0;
+    h->prof_launches = 0;
+    return ABM_OK;
+}
+
+int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches) {
+    if (!h || !total_ms || !launches) return ABM_ERR_ARG;
+    int rc = collect_profile(h);
+    if (rc) return rc;
+    *total_ms = h->prof_ms;
+    *launches = h->prof_launches;
+    return ABM_OK;
+}
+
+int64_t abm_current_step(abm_handle* h) { return h ? h->k : -1; }
+int64_t abm_launch_count(abm_handle* h) { return h ? h->launches : -1; }
+
+void abm_destroy(abm_handle* h) {
+    if (!h) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
+    for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (void* p : h->owned) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,659 @@
+// abm_kernels.cuh -- sm_100a kernels of the covid19_abm agent step.
+//
+// One launch of abm_substep_kernel per 4-hour sub-step does, for every agent slot, in this order:
+//   I(k-1)  infection draw of the previous sub-step against the district x status threshold table and the
+//           household hazard (reference: EpidemicScheduler.step location loop, base_model.py:60-175, in
+//           its pressure-table form) and, on infection, the whole disease course
+//           (Country.set_epidemic_status, base_model.py:838-1055)
+//   log     the four "current" counters of Country.log_model_output (base_model.py:1092-1095) at hour 8
+//   T(k)    time-to-next-event transitions (update_agent_states, base_model.py:226-272) and the
+//           contagious promotion (base_model.py:54-58)
+//   M(k)    go_home at hour 16 / go_out + OD mobility at hour 8 (base_model.py:274-441)
+//   A(k)    accumulation of the district x status infectious-pressure and headcount tables
+// Fusing I(k-1) into the launch of sub-step k means the 8-byte hot record of an agent is read once
+// per sub-step.  abm_hazard_table_kernel then turns the accumulated tables into 31-bit Bernoulli
+// thresholds for the next launch.
+//
+// All random numbers are Philox4x32-10 keyed (seed; agent id, sub-step, site).  Everything that is
+// compared against the oracle is integer arithmetic or IEEE double +,*,/ through the __d*_rn
+// intrinsics (never contracted to FMA), so results are bit-identical to oracle/abm_oracle.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/abm_b200.h"
+
+namespace abm {
+
+// ---- flags word (constants.py F_*)
+constexpr uint32_t F_EPI_MASK = 0x7u, F_CLIN_SHIFT = 3, F_CLIN_MASK = 0x3u, F_SYM_SHIFT = 5, F_SYM_MASK = 0x3u;
+constexpr uint32_t F_LOC_SHIFT = 7, F_LOC_MASK = 0x7u;
+constexpr uint32_t F_AWAY = 1u << 10, F_DMOVER = 1u << 11;
+constexpr uint32_t F_STATUS_SHIFT = 12, F_STATUS_MASK = 0xFu, F_AGE_SHIFT = 16, F_AGE_MASK = 0x7Fu;
+constexpr uint32_t F_HEAD = 1u << 23, F_OUT_H = 1u << 24, F_OUT_C = 1u << 25, F_OUT_D = 1u << 26, F_ONSET = 1u << 27;
+constexpr uint32_t F_EKIND_SHIFT = 28, F_EKIND_MASK = 0x3u, F_BIGHH = 1u << 30, F_FILLER = 1u << 31;
+constexpr uint32_t LOC_HOME = 0, LOC_ECON = 1, LOC_DIST = 2, LOC_HOSP = 3, LOC_DEAD = 4;
+constexpr uint32_t EKIND_HOUSEHOLD = 0, EKIND_HOME_DISTRICT = 1, EKIND_POOL = 2;
+constexpr uint32_t EPI_S = 0, EPI_I = 1, EPI_C = 2, EPI_R = 3, EPI_D = 4;
+constexpr int32_t T_NEVER = 0x7FFFFFFF;
+constexpr uint32_t FIRE_NEVER = 0xFFFFu;
+constexpr int32_t DAY = 1440;
+
+// ---- step modes
+constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32;
+
+// ---- cumulative counters (device array cum[])
+enum { CUM_CONTAGIOUS = 0, CUM_INFECTED, CUM_HOSPITALIZED, CUM_CRITICAL, CUM_DIED, CUM_RECOVERED, CUM_ASYM, CUM_SYM,
+       CUR_EXPOSED, CUR_CONTAGIOUS, CUR_HOSPITALIZED, CUR_CRITICAL, N_TALLY };
+
+constexpr int THREADS = 256;
+constexpr int PER_THREAD = 4;
+static_assert(THREADS * PER_THREAD == ABM_TILE, "one tile per block");
+
+struct DevTables {
+    const uint32_t* rfx; const uint32_t* qfx; const double* W; const double* pool_hw;
+    const uint32_t* od_thr; const double* stay_par; const uint32_t* dwell; const int32_t* znorm;
+    const double* p_hosp; const double* p_crit; const double* p_hfat; const double* severe_risk;
+    const uint32_t* move_thr; const int64_t* district_start; const int64_t* tile_base;
+    const uint16_t* tile_home; const int64_t* big_start;
+    int32_t D, A, P, hw_rows, n_big, step_ticks, mild_active;
+    uint32_t seed_lo, seed_hi;
+    double symptomatic_rate, critical_fatality_rate;
+};
+
+struct DevAgents {
+    uint32_t* flags; uint32_t* aux;
+    int32_t* t_infected; int32_t* t_contagious; int32_t* t_onset; int32_t* t_recovered; int32_t* t_return;
+    uint32_t* inf_at; const uint16_t* move_class; const uint32_t* econ_pool;
+};
+
+struct DevWork {
+    unsigned long long* acc;        // [2][P][A]: R fixed-point sums, then head counts
+    const uint32_t* thr_out;        // [P][A] thresholds from the previous sub-step
+    unsigned long long* hbig_read;  // [n_big] household hazard of big households, previous sub-step
+    unsigned long long* hbig_write; // [n_big] accumulated this sub-step
+    unsigned long long* cum;        // [N_TALLY]
+    long long* log_row;             // day-log row written when M_LOG
+};
+
+struct StepArgs {
+    int32_t k;        // sub-step being executed (T/M/A phases)
+    int32_t now;      // its minute tick
+    int32_t k_inf;    // sub-step whose infection draw is applied (k - 1)
+    int32_t now_inf;
+    uint32_t mode;
+    int32_t weekday;  // 0..6 of `now`
+};
+
+// ------------------------------------------------------------------------------------------------ Philox
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ U4 agent_draws(const DevTables& T, int64_t cid, int32_t step, uint32_t site) {
+    return philox4x32_10((uint32_t)cid, (uint32_t)((uint64_t)cid >> 32), (uint32_t)step, site, T.seed_lo, T.seed_hi);
+}
+
+// Bernoulli with probability p on a 32-bit draw: (x >> 1) / 2^31 < p, as an exact double comparison.
+__device__ __forceinline__ bool bernoulli(uint32_t x, double p) {
+    return (double)(x >> 1) < __dmul_rn(p, 2147483648.0);
+}
+
+// Integer inverse-CDF lookup (oracle.sample_quantile): [2][QN+1] knots, last bin refined by row 1.
+__device__ __forceinline__ uint32_t sample_quantile_u32(const uint32_t* __restrict__ t2, uint32_t x) {
+    const uint32_t i = x >> 20, f = x & 0xFFFFFu;
+    if (i < ABM_QN - 1) {
+        const uint64_t lo = __ldg(t2 + i), hi = __ldg(t2 + i + 1);
+        return (uint32_t)(lo + (((hi - lo) * f) >> 20));
+    }
+    const uint32_t j = f >> 8, g = f & 0xFFu;
+    const uint64_t lo = __ldg(t2 + (ABM_QN + 1) + j), hi = __ldg(t2 + (ABM_QN + 1) + j + 1);
+    return (uint32_t)(lo + (((hi - lo) * g) >> 8));
+}
+
+// 1 - exp(-x), x >= 0: fixed sequence of IEEE double ops (oracle.one_minus_exp_neg).
+__device__ __forceinline__ double horner_omexp(double y) {
+    double s = 1.0;
+#pragma unroll
+    for (int n = 20; n > 1; --n) s = __dsub_rn(1.0, __dmul_rn(__dmul_rn(y, 1.0 / (double)n), s));
+    return __dmul_rn(y, s);
+}
+__device__ __forceinline__ double one_minus_exp_neg(double x) {
+    x = fmin(x, 40.0);
+    if (x < 0.5) return horner_omexp(x);
+    double e = __dsub_rn(1.0, horner_omexp(__dmul_rn(x, 0.015625)));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e = __dmul_rn(e, e);
+    return __dsub_rn(1.0, e);
+}
+__device__ __forceinline__ uint32_t hazard_threshold(double x) {
+    return (uint32_t)ceil(__dmul_rn(one_minus_exp_neg(x), 2147483648.0));
+}
+
+__device__ __forceinline__ uint32_t fire_index(int32_t t, int32_t step_ticks) {
+    if (t == T_NEVER) return FIRE_NEVER;
+    if (t < 0) return 0;
+    const uint32_t f = (uint32_t)(t / step_ticks) + 1u;
+    return f < 0xFFFEu ? f : 0xFFFEu;
+}
+
+// home district from the canonical id (agents are sorted by home district)
+__device__ __forceinline__ uint32_t district_of(const DevTables& T, int64_t cid) {
+    int lo = 0, hi = T.D;           // district_start[lo] <= cid < district_start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(T.district_start + mid) <= cid) lo = mid; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+__device__ __forceinline__ uint32_t home_district(const DevTables& T, uint32_t f, uint32_t a, int64_t cid) {
+    return (f & F_AWAY) ? district_of(T, cid) : (a >> 16);
+}
+__device__ __forceinline__ int big_slot(const DevTables& T, int64_t cid) {
+    int lo = 0, hi = T.n_big;       // big_start[lo] <= cid < big_start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(T.big_start + mid) <= cid) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool at_own_household(uint32_t f) {
+    const uint32_t kind = (f >> F_LOC_SHIFT) & F_LOC_MASK;
+    return kind == LOC_HOME || (kind == LOC_ECON && ((f >> F_EKIND_SHIFT) & F_EKIND_MASK) == EKIND_HOUSEHOLD);
+}
+
+// Outside pool (row of the district x status tables) the agent is currently in, or -1.
+// Hospital is location -current_district (base_model.py:270-272): district 0 maps onto its own outside
+// pool (quirk Q3); every other hospital / the dead location holds no susceptible agent.
+__device__ __forceinline__ int pool_of(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int64_t cid) {
+    const uint32_t kind = (f >> F_LOC_SHIFT) & F_LOC_MASK;
+    if (kind == LOC_ECON) {
+        const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
+        if (ek == EKIND_HOME_DISTRICT) return (int)home_district(T, f, a, cid);
+        if (ek == EKIND_POOL) return (int)__ldg(G.econ_pool + slot);
+        return -1;
+    }
+    if (kind == LOC_DIST) return (int)(a >> 16);
+    if (kind == LOC_HOSP) return (a >> 16) == 0 ? 0 : -1;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------ infection event
+// Country.set_epidemic_status for one agent (base_model.py:838-1055).  Returns the new flags; writes the
+// cold vectors; *t_next gets the sub-step at which the first scheduled event fires (>= k_first).
+__device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+                                                 int64_t cid, int32_t k_inf, int32_t now_inf, uint32_t k_first,
+                                                 unsigned int* s_tally) {
+    const U4 A4 = agent_draws(T, cid, k_inf, 1u);
+    const U4 B4 = agent_draws(T, cid, k_inf, 2u);
+    const uint32_t age = (f >> F_AGE_SHIFT) & F_AGE_MASK;
+    const uint32_t cur = a >> 16;
+    const bool sym = bernoulli(A4.x, T.symptomatic_rate);                                  // :853-857
+    int32_t t_c, t_o, t_r;
+    uint32_t out = 0;
+    if (sym) {
+        t_o = now_inf + (int32_t)sample_quantile_u32(T.dwell + 0 * 2 * (ABM_QN + 1), A4.y); // :868-878
+        t_c = t_o - 12 * 60;                                                                // :880-882
+        const double p_h = __dmul_rn(__ldg(T.p_hosp + age), __ldg(T.severe_risk + cur));    // :885-896
+        const bool hosp = bernoulli(A4.z, p_h);                                             // :898-901
+        const bool crit = hosp && bernoulli(A4.w, __ldg(T.p_crit + age));                   // :903-912
+        const bool dies = crit ? bernoulli(B4.x, T.critical_fatality_rate)                  // :919-921
+                               : (hosp && bernoulli(B4.y, __ldg(T.p_hfat + age)));          // :923-933
+        if (hosp) out |= F_OUT_H;
+        if (crit) out |= F_OUT_C;
+        if (dies) out |= F_OUT_D;
+        if (dies) t_r = T_NEVER;                                                            // :967-994
+        else if (crit) t_r = t_o + 21 * DAY;                                                // :996-1000
+        else if (hosp) t_r = t_o + 13 * DAY;                                                // :1002-1006
+        else t_r = t_o + (int32_t)sample_quantile_u32(T.dwell + 2 * 2 * (ABM_QN + 1), B4.z); // :1008-1022
+        atomicAdd(s_tally + CUM_SYM, 1u);
+    } else {                                                                                // :1024-1055
+        t_o = T_NEVER;
+        t_c = now_inf + (int32_t)sample_quantile_u32(T.dwell + 1 * 2 * (ABM_QN + 1), A4.y);
+        t_r = t_c + (int32_t)sample_quantile_u32(T.dwell + 3 * 2 * (ABM_QN + 1), B4.z);
+        atomicAdd(s_tally + CUM_ASYM, 1u);
+    }
+    G.t_infected[slot] = now_inf;                                                           // :851
+    G.t_contagious[slot] = t_c;
+    G.t_onset[slot] = t_o;
+    G.t_recovered[slot] = t_r;
+    G.inf_at[slot] = (((f >> F_LOC_SHIFT) & F_LOC_MASK) << 16) | cur;                       // :846-847
+    f &= ~(F_EPI_MASK | (F_SYM_MASK << F_SYM_SHIFT) | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
+    f |= EPI_I | ((sym ? 2u : 1u) << F_SYM_SHIFT) | out;                                    // :850
+    // earliest scheduled event (contagious always precedes the others except when onset < 12 h)
+    uint32_t fi = fire_index(t_c, T.step_ticks);
+    const uint32_t fo = fire_index(t_o, T.step_ticks), fr = fire_index(t_r, T.step_ticks);
+    fi = fi < fo ? fi : fo;
+    fi = fi < fr ? fi : fr;
+    fi = fi > k_first ? fi : k_first;
+    a = (a & 0xFFFF0000u) | fi;
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------ transitions
+// update_agent_states (base_model.py:226-272) + contagious promotion (base_model.py:54-58) for one agent
+// whose next-event index is due.  Cumulative date counters are tallied the first time a date is passed.
+__device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+                                                     int32_t now, unsigned int* s_tally) {
+    const int32_t t_c = G.t_contagious[slot], t_o = G.t_onset[slot], t_r = G.t_recovered[slot];
+    const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
+    const int32_t t_cs = (f & F_OUT_C) ? t_o + 13 * DAY : T_NEVER;  // hospital end = critical start (base_model.py:953)
+    const int32_t t_d = (f & F_OUT_D) ? t_o + 21 * DAY : T_NEVER;   // params.py:177 (== end of critical care when critical)
+    uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = (f >> F_LOC_SHIFT) & F_LOC_MASK;
+    if (t_c < now && epi == EPI_I) atomicAdd(s_tally + CUM_CONTAGIOUS, 1u);
+    if (t_d < now && epi < EPI_D) {                                  // :230-237
+        epi = EPI_D; loc = LOC_DEAD; clin = 3;
+        atomicAdd(s_tally + CUM_DIED, 1u);
+    }
+    if (t_r < now && epi < EPI_R) {                                  // :240-254
+        epi = EPI_R;
+        if (t_h < now) loc = LOC_HOME;
+        clin = 3;
+        atomicAdd(s_tally + CUM_RECOVERED, 1u);
+    }
+    if (t_cs < now && clin < 2) { clin = 2; atomicAdd(s_tally + CUM_CRITICAL, 1u); }      // :257-261
+    if (t_h < now && clin < 1) { clin = 1; loc = LOC_HOSP; atomicAdd(s_tally + CUM_HOSPITALIZED, 1u); }  // :263-272
+    if (t_o < now) f |= F_ONSET;                                     // :212-219 (symptom onset passed)
+    if (t_c < now && epi < EPI_C) epi = EPI_C;                       // :54-58
+    f = (f & ~(F_EPI_MASK | (F_CLIN_MASK << F_CLIN_SHIFT) | (F_LOC_MASK << F_LOC_SHIFT))) | epi | (clin << F_CLIN_SHIFT) |
+        (loc << F_LOC_SHIFT);
+    uint32_t nf = FIRE_NEVER;
+    const int32_t ts[6] = {t_c, t_o, t_h, t_cs, t_d, t_r};
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (ts[i] >= now) { const uint32_t x = fire_index(ts[i], T.step_ticks); nf = x < nf ? x : nf; }
+    a = (a & 0xFFFF0000u) | nf;
+    return f;
+}
+
+__device__ __forceinline__ bool is_active(uint32_t f, uint32_t a) {
+    // get_active_ids (base_model.py:198-209): not hospitalised or recovered, at a non-negative location
+    const uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = (f >> F_LOC_SHIFT) & F_LOC_MASK;
+    const bool loc_ok = !(loc == LOC_DEAD || (loc == LOC_HOSP && (a >> 16) != 0));
+    return (clin < 1 || epi == EPI_R) && loc_ok;
+}
+
+// go_out for one active agent (base_model.py:304-441).
+__device__ __forceinline__ uint32_t go_out_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+                                                 int64_t cid, const StepArgs& s) {
+    const bool weekday = (s.mode & M_WEEKDAY) != 0;                                         // :309-312
+    const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;           // :212-219, :316
+    const uint32_t thr = __ldg(T.move_thr + 4 * (uint32_t)__ldg(G.move_class + slot) + (weekday ? 0 : 2) + (mild ? 1 : 0));
+    if (thr == 0) return f;
+    const bool away = (f & F_AWAY) != 0;
+    const bool needs_od = (f & F_DMOVER) != 0;
+    U4 X = U4{0, 0, 0, 0};
+    if (thr < 0x80000000u || needs_od) X = agent_draws(T, cid, s.k, 0u);
+    if (!((X.y >> 1) < thr)) return f;                                                      // :317-318 not a mover
+    bool returning = false;
+    if (away && G.t_return[slot] < s.now) {                                                 // :342-360
+        returning = true;
+        f &= ~F_AWAY;
+        a = (a & 0xFFFFu) | (district_of(T, cid) << 16);
+    }
+    bool left = false;
+    if (needs_od && !(f & F_AWAY)) {                                                        // :366-370
+        const uint32_t home = a >> 16;
+        const uint32_t* row = T.od_thr + ((size_t)s.weekday * T.D + home) * T.D;
+        const uint32_t u = X.z >> 1;
+        // first column j with u < thr[j] (rows are non-decreasing); none -> column 0 (quirk Q8)   :372-377
+        int lo = 0, hi = T.D;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (u < __ldg(row + mid)) hi = mid; else lo = mid + 1;
+        }
+        const uint32_t dest = lo < T.D ? (uint32_t)lo : 0u;
+        if (dest != home) {                                                                 // :410-439
+            const double* par = T.stay_par + (((size_t)s.weekday * T.D + home) * T.D + dest) * 3;
+            const uint32_t mag_x = X.w << 1;
+            const uint32_t i = mag_x >> 20, fr = mag_x & 0xFFFFFu;
+            int64_t mag;
+            if (i < ABM_QN - 1) {
+                const int64_t zl = __ldg(T.znorm + i), zh = __ldg(T.znorm + i + 1);
+                mag = zl + (((zh - zl) * (int64_t)fr) >> 20);
+            } else {
+                const uint32_t j = fr >> 8, g = fr & 0xFFu;
+                const int64_t zl = __ldg(T.znorm + (ABM_QN + 1) + j), zh = __ldg(T.znorm + (ABM_QN + 1) + j + 1);
+                mag = zl + (((zh - zl) * (int64_t)g) >> 8);
+            }
+            const double z = __dmul_rn((double)((X.w >> 31) ? -mag : mag), 1.0 / 65536.0);
+            const double t = __dadd_rn(__ldg(par + 1), __dmul_rn(__ldg(par + 2), z));
+            const double hours = __dmul_rn(__ldg(par + 0), __dmul_rn(__dmul_rn(t, t), t));
+            const double m = floor(fmin(fmax(__dmul_rn(hours, 60.0), 0.0), 1.0e9));
+            const int64_t ret = (int64_t)s.now + (int64_t)m;
+            G.t_return[slot] = (int32_t)(ret < (int64_t)T_NEVER - 1 ? ret : (int64_t)T_NEVER - 1);
+            f |= F_AWAY;
+            a = (a & 0xFFFFu) | (dest << 16);
+            f = (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_DIST << F_LOC_SHIFT);
+            left = true;
+        }
+    }
+    if (!left) f = (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_ECON << F_LOC_SHIFT);           // :331-339, :346-352
+    (void)returning;
+    return f;
+}
+
+// go_home for one active agent (base_model.py:274-302).
+__device__ __forceinline__ uint32_t go_home_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+                                                  int64_t cid, const StepArgs& s) {
+    if (!(f & F_AWAY)) return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
+    if (G.t_return[slot] < s.now) {
+        f &= ~F_AWAY;
+        a = (a & 0xFFFFu) | (district_of(T, cid) << 16);
+        return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+__global__ void __launch_bounds__(THREADS, 4)
+abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
+    __shared__ uint16_t s_code[ABM_TILE];          // household walk: bit15 head, bit14 contagious at home, low 8 sym|age
+    __shared__ unsigned int s_tally[N_TALLY];
+    __shared__ unsigned int s_cnt[ABM_MAX_STATUS];
+    __shared__ unsigned long long s_r[ABM_MAX_STATUS];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t tile = blockIdx.x;
+    const int64_t slot0 = tile * ABM_TILE + (int64_t)tid * PER_THREAD;
+    const int64_t tbase = __ldg(T.tile_base + tile);
+    const int tcount = (int)(__ldg(T.tile_base + tile + 1) - tbase);
+    const int64_t cid0 = tbase + (int64_t)tid * PER_THREAD;
+
+    if (tid < N_TALLY) s_tally[tid] = 0;
+    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_r[tid] = 0ull; }
+
+    const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
+    uint32_t f[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
+    uint32_t a[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
+    const uint32_t f_in[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
+    const uint32_t a_in[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
+
+    // ---------------------------------------------------------------- I(k-1): infection draw
+    if (s.mode & M_INFECT) {
+        bool any_cont_home = false;
+        uint16_t code[PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const uint32_t fj = f[j];
+            const bool ch = (fj & F_EPI_MASK) == EPI_C && at_own_household(fj) && !(fj & F_BIGHH);
+            any_cont_home |= ch;
+            code[j] = (uint16_t)(((fj & F_HEAD) ? 0x8000u : 0u) | (ch ? 0x4000u : 0u) |
+                                 ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 0x80u : 0u) | ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+        }
+        const int tile_has_cont_home = __syncthreads_or(any_cont_home);
+        if (tile_has_cont_home) {
+            *reinterpret_cast<uint2*>(s_code + tid * PER_THREAD) =
+                make_uint2((uint32_t)code[0] | ((uint32_t)code[1] << 16), (uint32_t)code[2] | ((uint32_t)code[3] << 16));
+            __syncthreads();
+        }
+        unsigned long long hsum = 0ull;
+        bool hvalid = false;
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            uint32_t fj = f[j];
+            if (fj & F_HEAD) hvalid = false;
+            if ((fj & F_EPI_MASK) != EPI_S) continue;
+            const int64_t slot = slot0 + j, cid = cid0 + j;
+            uint32_t thr = 0;
+            if (at_own_household(fj)) {
+                unsigned long long hz = 0ull;
+                if (fj & F_BIGHH) {
+                    hz = Wk.hbig_read[big_slot(T, cid)];
+                } else if (tile_has_cont_home) {
+                    if (!hvalid) {
+                        int o = tid * PER_THREAD + j;
+                        int b = o;
+                        while (b > 0 && !(s_code[b] & 0x8000u)) --b;
+                        const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, a[j], cid) : 0u;
+                        const uint32_t* q = T.qfx + (size_t)qrow * 256;
+                        hsum = 0ull;
+                        int e = b;
+                        do {
+                            const uint32_t c = s_code[e];
+                            if (c & 0x4000u) hsum += __ldg(q + (c & 0xFFu));
+                            ++e;
+                        } while (e < ABM_TILE && !(s_code[e] & 0x8000u));
+                        hvalid = true;
+                        (void)o;
+                    }
+                    hz = hsum;
+                }
+                if (hz) thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0));
+            } else {
+                const int pool = pool_of(T, G, fj, a[j], slot, cid);
+                if (pool >= 0) thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
+            }
+            if (thr) {
+                const U4 X = agent_draws(T, cid, s.k_inf, 0u);
+                if ((X.x >> 1) < thr) {
+                    f[j] = infect_agent(T, G, fj, a[j], slot, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+                    atomicAdd(s_tally + CUM_INFECTED, 1u);
+                }
+            }
+        }
+    } else {
+        __syncthreads();   // s_tally / s_cnt initialisation
+    }
+
+    if (s.mode & M_STEP) {
+        // ------------------------------------------------------------ log: "current" counters before T(k)
+        if (s.mode & M_LOG) {
+            uint32_t c = 0;   // 4 x 8-bit packed counts (<= 4 each)
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; ++j) {
+                const uint32_t epi = f[j] & F_EPI_MASK, clin = (f[j] >> F_CLIN_SHIFT) & F_CLIN_MASK;
+                c += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+            }
+            c = __reduce_add_sync(0xFFFFFFFFu, c);   // <= 128 per field
+            if (lane < 4) {
+                const unsigned int v = (c >> (8 * lane)) & 0xFFu;
+                if (v) atomicAdd(s_tally + CUR_EXPOSED + lane, v);
+            }
+        }
+        // ------------------------------------------------------------ T(k) transitions, M(k) movement
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const int64_t slot = slot0 + j, cid = cid0 + j;
+            if ((a[j] & 0xFFFFu) <= (uint32_t)s.k) f[j] = transition_agent(T, G, f[j], a[j], slot, s.now, s_tally);
+            if ((s.mode & (M_GO_OUT | M_GO_HOME)) && !(f[j] & F_FILLER) && is_active(f[j], a[j])) {
+                if (s.mode & M_GO_HOME) f[j] = go_home_agent(T, G, f[j], a[j], slot, cid, s);
+                if (s.mode & M_GO_OUT) f[j] = go_out_agent(T, G, f[j], a[j], slot, cid, s);
+            }
+        }
+        // ------------------------------------------------------------ A(k): pressure / headcount tables
+        const int L0 = (int)__ldg(T.tile_home + tile);
+        uint32_t cw[3] = {0, 0, 0};
+        int pool[PER_THREAD];
+        bool cont_any = false;
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const uint32_t fj = f[j];
+            const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
+            pool[j] = pool_of(T, G, fj, a[j], slot0 + j, cid0 + j);
+            const bool cont = (fj & F_EPI_MASK) == EPI_C;
+            if (pool[j] == L0) {
+                const uint32_t inc = 1u << (8 * (st & 3));
+                if ((st >> 2) == 0) cw[0] += inc; else if ((st >> 2) == 1) cw[1] += inc; else cw[2] += inc;
+                cont_any |= cont;
+            } else if (pool[j] >= 0) {
+                atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)pool[j] * T.A + st, 1ull);
+                if (cont) {
+                    const uint32_t r = __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+                    atomicAdd(Wk.acc + (size_t)pool[j] * T.A + st, (unsigned long long)r);
+                }
+            }
+            if (cont && (fj & F_BIGHH) && at_own_household(fj)) {
+                const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, a[j], cid0 + j) : 0u;
+                const uint32_t q = __ldg(T.qfx + (size_t)qrow * 256 + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+                atomicAdd(Wk.hbig_write + big_slot(T, cid0 + j), (unsigned long long)q);
+            }
+        }
+        // head counts: 3 packed warp reductions, lane b keeps status b
+        const uint32_t w0 = __reduce_add_sync(0xFFFFFFFFu, cw[0]);
+        const uint32_t w1 = __reduce_add_sync(0xFFFFFFFFu, cw[1]);
+        const uint32_t w2 = __reduce_add_sync(0xFFFFFFFFu, cw[2]);
+        if (lane < T.A) {
+            const uint32_t w = (lane >> 2) == 0 ? w0 : ((lane >> 2) == 1 ? w1 : w2);
+            const unsigned int v = (w >> (8 * (lane & 3))) & 0xFFu;
+            if (v) atomicAdd(s_cnt + lane, v);
+        }
+        // infectious pressure: only warps that hold a contagious agent in the tile's home pool
+        if (__any_sync(0xFFFFFFFFu, cont_any)) {
+            for (int b = 0; b < T.A; ++b) {
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int j = 0; j < PER_THREAD; ++j) {
+                    const uint32_t fj = f[j];
+                    if (pool[j] == L0 && (fj & F_EPI_MASK) == EPI_C && (int)((fj >> F_STATUS_SHIFT) & F_STATUS_MASK) == b) {
+                        const uint32_t r = __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+                        lo += r & 0xFFFFu; hi += r >> 16;
+                    }
+                }
+                lo = __reduce_add_sync(0xFFFFFFFFu, lo);
+                hi = __reduce_add_sync(0xFFFFFFFFu, hi);
+                if (lane == 0 && (lo | hi)) atomicAdd(s_r + b, ((unsigned long long)hi << 16) + lo);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- write back what changed
+    if (f[0] != f_in[0] || f[1] != f_in[1] || f[2] != f_in[2] || f[3] != f_in[3])
+        *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f[0], f[1], f[2], f[3]);
+    if (a[0] != a_in[0] || a[1] != a_in[1] || a[2] != a_in[2] || a[3] != a_in[3])
+        *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a[0], a[1], a[2], a[3]);
+
+    __syncthreads();
+    if (tid < N_TALLY) {
+        const unsigned int v = s_tally[tid];
+        if (v) {
+            if (tid < CUR_EXPOSED) atomicAdd(Wk.cum + tid, (unsigned long long)v);
+            else atomicAdd(reinterpret_cast<unsigned long long*>(Wk.log_row) + (ABM_C_CURRENT_EXPOSED_CASES + tid - CUR_EXPOSED),
+                           (unsigned long long)v);
+        }
+    }
+    if ((s.mode & M_STEP) && tid >= 32 && tid < 32 + ABM_MAX_STATUS) {
+        const int b = tid - 32;
+        const int L0 = (int)__ldg(T.tile_home + tile);
+        if (b < T.A) {
+            if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)L0 * T.A + b, (unsigned long long)s_cnt[b]);
+            if (s_r[b]) atomicAdd(Wk.acc + (size_t)L0 * T.A + b, s_r[b]);
+        }
+    }
+    (void)tcount;
+}
+
+// ------------------------------------------------------------------------------------------------ table kernel
+// District x status tables -> infection thresholds:
+//   lambda[L][b] = hw[L] * (sum_a W[a][b] * R[L][a]) / Ncnt[L][b],  thr = ceil((1 - exp(-lambda)) * 2^31)
+// then clears the accumulators for the next sub-step, snapshots them for inspection, and at log
+// sub-steps copies the cumulative counters into the day-log row.
+struct TableArgs {
+    int32_t write_log;
+    int32_t tick;
+    long long seeds_before_now;
+};
+
+__global__ void abm_hazard_table_kernel(const DevTables T, unsigned long long* acc, unsigned long long* acc_snapshot,
+                                        uint32_t* thr_out, unsigned long long* hbig_clear, const unsigned long long* cum,
+                                        long long* log_row, const TableArgs ta) {
+    const int n = T.P * T.A;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int L = i / T.A, b = i - L * T.A;
+        const unsigned long long cnt = acc[n + i];
+        uint32_t thr = 0;
+        if (cnt) {
+            double sum = 0.0;
+            for (int a = 0; a < T.A; ++a)
+                sum = __dadd_rn(sum, __dmul_rn(__ldg(T.W + a * T.A + b), (double)acc[L * T.A + a]));
+            const double lam = __dmul_rn(__ldg(T.pool_hw + L), __ddiv_rn(sum, (double)cnt));
+            thr = hazard_threshold(lam);
+        }
+        thr_out[i] = thr;
+    }
+    if (i < T.n_big) hbig_clear[i] = 0ull;
+    if (blockIdx.x == 0 && ta.write_log && threadIdx.x < 8) {
+        const int t = threadIdx.x;
+        // cumulative date counters (base_model.py:1089-1090, 1097-1103)
+        if (t < 6) log_row[t] = (long long)cum[t] + (t == CUM_INFECTED ? ta.seeds_before_now : 0);
+        if (t == 6) log_row[ABM_C_ASYMPTOMATIC_COUNT] = (long long)cum[CUM_ASYM];
+        if (t == 7) { log_row[ABM_C_SYMPTOMATIC_COUNT] = (long long)cum[CUM_SYM]; log_row[ABM_C_TICK] = ta.tick; }
+    }
+}
+
+// second pass of the table kernel: snapshot + clear (separate launch so every thread of the first
+// pass has read the full row of R before it is zeroed)
+__global__ void abm_clear_tables_kernel(unsigned long long* acc, unsigned long long* acc_snapshot, int n2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) { acc_snapshot[i] = acc[i]; acc[i] = 0ull; }
+}
+
+// ------------------------------------------------------------------------------------------------ seeding
+__global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned long long* cum, const int64_t* slots,
+                                const int64_t* ids, int64_t n, int32_t k, int32_t now) {
+    __shared__ unsigned int s_tally[N_TALLY];
+    if (threadIdx.x < N_TALLY) s_tally[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t slot = slots[i];
+        uint32_t a = G.aux[slot];
+        const uint32_t f = infect_agent(T, G, G.flags[slot], a, slot, ids[i], k, now, (uint32_t)k, s_tally);
+        G.flags[slot] = f;
+        G.aux[slot] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == CUM_ASYM || threadIdx.x == CUM_SYM) {
+        const unsigned int v = s_tally[threadIdx.x];
+        if (v) atomicAdd(cum + threadIdx.x, (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ district statistics
+// get_safe_and_unsafe_districts (base_model.py:733-758): symptomatic infected-or-contagious per home district.
+__global__ void abm_district_sym_kernel(const DevTables T, const DevAgents G, int64_t n_slots, unsigned long long* sym,
+                                        unsigned long long* pop) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const uint32_t f = G.flags[slot];
+    if (f & F_FILLER) return;
+    const int64_t tile = slot / ABM_TILE;
+    const int64_t cid = __ldg(T.tile_base + tile) + (slot - tile * ABM_TILE);
+    const uint32_t d = home_district(T, f, G.aux[slot], cid);
+    atomicAdd(pop + d, 1ull);
+    const uint32_t epi = f & F_EPI_MASK;
+    if ((epi == EPI_I || epi == EPI_C) && ((f >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) atomicAdd(sym + d, 1ull);
+}
+
+// current-state counters over all slots (abm_counters)
+__global__ void abm_count_state_kernel(const DevAgents G, int64_t n_slots, unsigned long long* out4) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    if (slot < n_slots) {
+        const uint32_t f = G.flags[slot];
+        const uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK;
+        c = (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+        const unsigned int v = (c >> (8 * lane)) & 0xFFu;
+        if (v) atomicAdd(out4 + lane, (unsigned long long)v);
+    }
+}
+
+}  // namespace abm

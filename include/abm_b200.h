@@ -1,0 +1,161 @@
+/*
+ * abm_b200.h -- C ABI of the B200 agent-step library (libabm_b200.so).
+ *
+ * The reference (worldbank/covid19-agent-based-model) is pure Python and has no FFI of its own; the seam
+ * this library sits behind is the object pair Country <-> Country.scheduler
+ * (/root/reference/src/covid19_abm/base_model.py:518) and the calls the Python layers make through it.
+ * Each entry point below names the reference interface it replaces.  All functions return 0 on
+ * success or a negative abm_status; abm_last_error() gives the message.  Plain pointers and sizes
+ * only: no torch types cross this boundary.
+ *
+ * Ownership: every per-agent buffer is allocated by the caller (torch tensors on the handle's device)
+ * and must outlive the handle; the library owns its constant tables, accumulators, streams/events and
+ * (multi-GPU) its NCCL communicator.  Threading: one host thread per handle; all device work is
+ * enqueued on the stream given at creation.
+ */
+#ifndef ABM_B200_H
+#define ABM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABM_TILE 1024            /* agent slots per tile (one thread block)                       */
+#define ABM_BIG_HOUSEHOLD 32     /* households above this size use the global-atomic path         */
+#define ABM_MAX_STATUS 12        /* economic statuses                                             */
+#define ABM_QN 4096              /* bins of the quantile tables                                    */
+#define ABM_N_COUNTERS 12        /* fields of Country.log_model_output (base_model.py:1086-1104)   */
+#define ABM_LOG_STRIDE 16        /* int64 words per day-log row                                    */
+
+typedef enum {
+    ABM_OK = 0,
+    ABM_ERR_ARG = -1,
+    ABM_ERR_CUDA = -2,
+    ABM_ERR_STATE = -3,
+    ABM_ERR_NCCL = -4
+} abm_status;
+
+/* order of the 12 counters in abm_counters()/day-log rows (names as in base_model.py:1086-1104) */
+enum {
+    ABM_C_CURRENT_CONTAGIOUS_COUNT = 0, /* sum(date_start_contagious < now)  */
+    ABM_C_INFECTED_COUNT = 1,           /* sum(date_infected < now)          */
+    ABM_C_HOSPITALIZED_COUNT = 2,
+    ABM_C_CRITICAL_COUNT = 3,
+    ABM_C_DIED_COUNT = 4,
+    ABM_C_RECOVERED_COUNT = 5,
+    ABM_C_CURRENT_EXPOSED_CASES = 6,    /* sum(epidemic_state == INFECTED)   */
+    ABM_C_CURRENT_CONTAGIOUS_CASES = 7,
+    ABM_C_CURRENT_HOSPITALIZED_CASES = 8,
+    ABM_C_CURRENT_CRITICAL_CASES = 9,
+    ABM_C_ASYMPTOMATIC_COUNT = 10,
+    ABM_C_SYMPTOMATIC_COUNT = 11,
+    ABM_C_TICK = 12                     /* minute tick of the log row        */
+};
+
+typedef struct abm_handle abm_handle;
+
+/* ParamsConfig scalars the step needs (params.py:127-136, 179-192, 199-215). */
+typedef struct {
+    int64_t n_slots;            /* padded agent slots on this rank, multiple of ABM_TILE            */
+    int64_t n_tiles;
+    int64_t agent_id_base;      /* canonical id of this rank's first agent (Philox key)             */
+    int32_t n_districts;        /* D                                                                */
+    int32_t n_status;           /* A <= ABM_MAX_STATUS                                              */
+    int32_t n_pools;            /* P = D + extra outside locations (schools)                        */
+    int32_t hw_rows;            /* 1, or D under HANDWASHING_RISK* (base_model.py:189-191)          */
+    int32_t n_move_classes;
+    int32_t n_big_households;
+    int32_t step_ticks;         /* minutes per sub-step (params.step_timedelta)                     */
+    int32_t start_minute_of_day;/* scheduler.real_time at step 0                                    */
+    int32_t start_weekday;      /* datetime.weekday() at step 0                                     */
+    int32_t mild_active;        /* MILD_SYMPTOM_MOVEMENT_PROBABILITY < 1                             */
+    int32_t max_log_rows;       /* capacity of the device day log                                   */
+    int32_t device;             /* CUDA device ordinal                                              */
+    uint64_t seed;              /* Philox key                                                       */
+    double symptomatic_rate;    /* params.SYMPTOMATIC_RATE                                          */
+    double critical_fatality_rate;
+    void* stream;               /* cudaStream_t to enqueue on (NULL = library-owned stream)         */
+    int32_t world_size;         /* ranks sharing the district tables (1 = no collective)            */
+    int32_t rank;
+    const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1            */
+} abm_config;
+
+/* Host pointers to the derived constant tables (abm_b200/tables.py); copied to the device. */
+typedef struct {
+    const uint32_t* rfx;          /* [2][128]  infection rate * 2^32 by (symptomatic, age)   params.py:236-242 */
+    const uint32_t* qfx;          /* [hw_rows][2][128]  -log(1 - 3 r hw) * 2^32              base_model.py:184-191 */
+    const double*   W;            /* [A][A]  k_a * M[a][b] * 2^-32                            params.py:278-297 */
+    const double*   pool_hw;      /* [P]     hand-washing multiplier of each outside pool               */
+    const uint32_t* od_thr;       /* [7][D][D] ceil(cumulative OD prob * 2^31)                params.py:252-259 */
+    const double*   stay_par;     /* [7][D][D][3] (mean h, a, b) of the stay transform        params.py:576-580 */
+    const uint32_t* dwell;        /* [4][2][QN+1] dwell quantiles, minutes                    params.py:145-189 */
+    const int32_t*  znorm;        /* [2][QN+1] half-normal quantile * 2^16                               */
+    const double*   p_hosp;       /* [128] AGE_HOSPITALIZATION_PROBABILITY                    params.py:223 */
+    const double*   p_crit;       /* [128] AGE_CRITICAL_CARE_PROBABILITY                      params.py:224 */
+    const double*   p_hfat;       /* [128] AGE_HOSPITALIZATION_FATALITY_PROBABILITY           params.py:225 */
+    const double*   severe_risk;  /* [D]   severe_disease_risk (ones under quirk Q2)          base_model.py:559 */
+    const uint32_t* move_thr;     /* [n_move_classes][4] mover thresholds                     base_model.py:316-318 */
+    const int64_t*  district_start;/* [D+1] canonical id of the first agent of each home district       */
+    const int64_t*  tile_base;    /* [n_tiles+1] canonical id of the first agent of each tile           */
+    const uint16_t* tile_home;    /* [n_tiles] home district of the first agent of each tile            */
+    const int64_t*  big_start;    /* [n_big_households+1] canonical id of first member (+ sentinel)     */
+} abm_tables;
+
+/* Device pointers of the caller-owned SoA agent store (Country's vectors, base_model.py:457-517). */
+typedef struct {
+    uint32_t* flags;        /* [n_slots] packed state word                       */
+    uint32_t* aux;          /* [n_slots] next-event sub-step | current district  */
+    int32_t*  t_infected;   /* date_infected                                     */
+    int32_t*  t_contagious; /* date_start_contagious                             */
+    int32_t*  t_onset;      /* date_start_symptomatic                            */
+    int32_t*  t_recovered;  /* date_recovered                                    */
+    int32_t*  t_return;     /* return_district_at                                */
+    uint32_t* inf_at;       /* infected_at_{district,location}_ids               */
+    const uint16_t* move_class; /* movement-probability class                    */
+    const uint32_t* econ_pool;  /* outside pool of EKIND_POOL agents, may be NULL */
+} abm_agent_ptrs;
+
+/* Country.__init__ + EpidemicScheduler.__init__ (base_model.py:24-31, 445-525). */
+int abm_create(const abm_config* cfg, abm_handle** out);
+/* ParamsConfig derived tables -> device (params.py:208-297). */
+int abm_set_tables(abm_handle* h, const abm_tables* t);
+/* Country.initialize_*_vectors (base_model.py:527-634): bind the caller's device buffers. */
+int abm_bind_agents(abm_handle* h, const abm_agent_ptrs* dev);
+/* Host hooks changed district_mover / movement probabilities / economic_activity_location_ids
+ * (base_model.py:642-731): new mover-threshold table (may be NULL = unchanged). */
+int abm_refresh(abm_handle* h, const uint32_t* move_thr, int32_t n_move_classes);
+/* Country.set_epidemic_status(ids) at scheduler.real_time (base_model.py:796, 838-1055).
+ * slots/ids are host arrays: slot index and canonical id of each agent to infect. */
+int abm_seed(abm_handle* h, const int64_t* slots, const int64_t* ids, int64_t n);
+/* n_substeps x EpidemicScheduler.step() (base_model.py:33-179); returns after enqueue. */
+int abm_step(abm_handle* h, int32_t n_substeps);
+/* Apply the infection draws of the last completed sub-step (they are otherwise fused into the next
+ * sub-step's kernel) so the agent vectors read exactly as after the reference's step(). */
+int abm_flush(abm_handle* h);
+/* Country.log_model_output rows produced so far (base_model.py:1082-1106): copies up to max_rows rows
+ * of ABM_LOG_STRIDE int64 (indices ABM_C_*) and returns the number of rows; synchronises. */
+int abm_read_log(abm_handle* h, int64_t* out, int32_t max_rows, int32_t* n_rows);
+/* The 12 counters at the current time, over this rank's agents (synchronises, flushes). */
+int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]);
+/* Country.get_safe_and_unsafe_districts inputs (base_model.py:733-758): per home district, number of
+ * symptomatic infected/contagious agents and population, over this rank's agents. */
+int abm_district_symptomatic(abm_handle* h, int64_t* sym, int64_t* pop);
+/* Device pointers of the district x status tables of the last sub-step: R (fixed-point infectious
+ * pressure, uint64 [P][A]), Ncnt (uint64 [P][A]) snapshot and thresholds (uint32 [P][A]); for tests. */
+int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* thr);
+/* Bracket every main-kernel launch with CUDA events (bench roofline); totals since last reset. */
+int abm_set_profiling(abm_handle* h, int32_t on);
+int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches);
+int64_t abm_current_step(abm_handle* h);
+int64_t abm_launch_count(abm_handle* h);
+int abm_sync(abm_handle* h);
+const char* abm_last_error(abm_handle* h);
+void abm_destroy(abm_handle* h);
+int abm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABM_B200_H */

@@ -45,7 +45,7 @@ def _fake_read_excel(status_names, matrix, sizes):
         if sheet_name == 'interaction_matrix':
             return pd.DataFrame(np.asarray(matrix, dtype=float), index=status_names, columns=status_names)
         if sheet_name == 'interactions':
-            return pd.DataFrame({'interactions': list(sizes)}, index=status_names)
+            return pd.DataFrame({'interactions': [int(v) for v in sizes]}, index=status_names)
         raise ValueError(sheet_name)
     return read_excel
 

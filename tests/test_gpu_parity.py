@@ -1,0 +1,151 @@
+"""CUDA path vs oracle / reference fixtures -- the parity tests proper (run on the B200 box).
+
+Everything goes through the C ABI (abm_b200.engine.Simulation -> libabm_b200.so).  Bar: bit-exact for
+every state, location and tick vector and for every log counter.
+"""
+import numpy as np
+import pytest
+
+from abm_b200 import synth, tables
+from oracle.abm_oracle import OracleModel
+from util import assert_state_equal, load_fixture, oracle_params, small_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _sim(spec, pop, seed, tab=None, **kw):
+    from abm_b200.engine import Simulation
+    return Simulation(spec, pop, seed=seed, device=0, tables=tab, **kw)
+
+
+@pytest.mark.parametrize('name', ['unmitigated', 'isolate_symptomatic', 'lockdown'])
+def test_cuda_matches_reference_fixture(built_library, name):
+    """CUDA state == state produced by the real reference functions (golden fixture), at every snapshot."""
+    fx = load_fixture(name)
+    spec, pop = fx['spec'], fx['pop']
+    sim = _sim(spec, pop, fx['philox_seed'])
+    sim.seed_infections(fx['seeds'])
+    done = 0
+    for k, snap in fx['snaps']:
+        sim.step(k - done)
+        done = k
+        assert_state_equal(sim.state(), snap, f'{name} after sub-step {k}')
+    log = sim.log_dicts()
+    assert len(log) == len(fx['ref_log'])
+    for got, want in zip(log, fx['ref_log']):
+        for key, val in want.items():
+            if key != 'date':
+                assert got[key] == val, (name, key, want['date'], got[key], val)
+        assert got['date'] == want['date']
+    sim.close()
+
+
+def test_cuda_matches_oracle_every_substep(built_library):
+    """Lock-step with the oracle for 12 simulated days, flushing after every sub-step."""
+    spec, pop, seeds, tab = small_case()
+    sim = _sim(spec, pop, 77, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 77)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    assert_state_equal(sim.state(), ora.state_dict(), 'after seeding')
+    for k in range(6 * 12):
+        sim.step(1)
+        ora.step()
+        assert_state_equal(sim.state(), ora.state_dict(), f'sub-step {k}')
+        r, n, t = sim.debug_tables()
+        assert np.array_equal(r, ora.last_tables['rsum']), f'pressure table, sub-step {k}'
+        assert np.array_equal(n, ora.last_tables['ncnt']), f'headcount table, sub-step {k}'
+        assert np.array_equal(t, ora.last_tables['thr_out']), f'threshold table, sub-step {k}'
+    sim.close()
+
+
+def test_fused_equals_flushed(built_library):
+    """Results do not depend on whether the infection draw is fused into the next launch or flushed."""
+    spec, pop, seeds, tab = small_case(n_agents=20_000, seed=9)
+    a, b = _sim(spec, pop, 5, tab), _sim(spec, pop, 5, tab)
+    a.seed_infections(seeds)
+    b.seed_infections(seeds)
+    a.step(6 * 10)
+    for _ in range(6 * 10):
+        b.step(1)
+        b.flush()
+    assert_state_equal(a.state(), b.state(), 'fused vs flushed')
+    assert np.array_equal(a.read_log(), b.read_log())
+    a.close(); b.close()
+
+
+def test_long_run_with_big_households_and_mild_symptoms(built_library):
+    """60 days incl. deaths; mining-camp sized households (atomic path) and symptomatic isolation."""
+    spec = synth.make_spec(n_districts=6, R0=2.8, seed=21, mild_symptom_move_prob=0.05)
+    pop = synth.make_population(25_000, spec, seed=21)
+    # merge runs of households into three big "camps" (scenario_models.py:232-236 does this for miners)
+    hh = pop.household.copy()
+    for lo in (1000, 9000, 17000):
+        hh[lo:lo + 400] = hh[lo]
+    _, pop.household = np.unique(hh, return_inverse=True)
+    pop.household = pop.household.astype(np.int64)
+    seeds = np.unique(np.concatenate([synth.pick_seeds(pop, spec, infect_num=250, seed=21), [1005, 9010, 17020]]))
+    tab = tables.build_tables(spec)
+    sim = _sim(spec, pop, 99, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 99)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    for day in range(60):
+        sim.step(6)
+        for _ in range(6):
+            ora.step()
+        if day % 10 == 9:
+            assert_state_equal(sim.state(), ora.state_dict(), f'day {day}')
+    got = sim.log_dicts()
+    assert len(got) == len(ora.log_rows)
+    for g, w in zip(got, ora.log_rows):
+        for key, val in w.items():
+            assert g[key] == val, (key, g['date'])
+    assert got[-1]['died_count'] > 0 and got[-1]['recovered_count'] > 1000
+    sim.close()
+
+
+def test_handwashing_risk_and_weekend(built_library):
+    """hw_risk multiplier per district (base_model.py:189-191) and a start on a Saturday."""
+    from datetime import datetime
+    spec = synth.make_spec(n_districts=7, R0=2.4, seed=31, start_datetime=datetime(2020, 9, 5, 8))
+    spec.hw_risk = np.random.default_rng(1).uniform(0.9, 1.1, spec.n_districts)
+    pop = synth.make_population(15_000, spec, seed=31)
+    seeds = synth.pick_seeds(pop, spec, infect_num=200, seed=31)
+    tab = tables.build_tables(spec)
+    sim = _sim(spec, pop, 3, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 3)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    sim.step(6 * 15)
+    for _ in range(6 * 15):
+        ora.step()
+    assert_state_equal(sim.state(), ora.state_dict(), 'hw risk, 15 days')
+    got = sim.log_dicts()
+    for g, w in zip(got, ora.log_rows):
+        for key, val in w.items():
+            assert g[key] == val, (key, g['date'])
+    sim.close()
+
+
+def test_counters_and_district_statistics(built_library):
+    spec, pop, seeds, tab = small_case(n_agents=20_000, seed=13)
+    sim = _sim(spec, pop, 8, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 8)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    sim.step(6 * 9)
+    for _ in range(6 * 9):
+        ora.step()
+    c = sim.counters()
+    assert c['current_exposed_cases'] == int((ora.epidemic_state == 1).sum())
+    assert c['current_contagious_cases'] == int((ora.epidemic_state == 2).sum())
+    assert c['asymptomatic_count'] == int((ora.infected_symptomatic_status == 0).sum())
+    assert c['symptomatic_count'] == int((ora.infected_symptomatic_status == 1).sum())
+    assert c['infected_count'] == int((ora.date_infected < ora.now()).sum())
+    sym, dpop = sim.district_symptomatic()
+    want_sym = np.bincount(pop.district[np.isin(ora.epidemic_state, [1, 2]) & (ora.infected_symptomatic_status == 1)],
+                           minlength=spec.n_districts)
+    assert np.array_equal(sym, want_sym)
+    assert np.array_equal(dpop, np.bincount(pop.district, minlength=spec.n_districts))
+    sim.close()
