@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- agent-days/s of the covid19_abm agent step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port on host cores)
+
+A "step" is one simulated day = 6 four-hour sub-steps (params.py:127) of the synthetic Zimbabwe-shaped
+population: 15 M agents per GPU, 60 districts, unmitigated, R0 = 1.9 (BASELINE.json configs[1]); N GPUs hold
+N x 15 M agents (weak scaling), sharded on household boundaries, one NCCL all-reduce of the
+district x status tables per sub-step.  Before the warm-up the epidemic is advanced (untimed) for
+--spinup days so the timed days run at substantial prevalence, the expensive regime for every
+implementation.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'covid19-agent-based-model_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = 'agent_days_per_sec'
+UNIT = 'agent-days/s'
+ALGO_BYTES_PER_AGENT_DAY = 104.0      # 6 x 16 B hot record + 2 x 4 B movement write-back
+SUBSTEPS_PER_DAY = 6
+POP_SEED = 2020
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--agents-per-gpu', type=int, default=15_000_000)
+    ap.add_argument('--districts', type=int, default=60)
+    ap.add_argument('--spinup', type=int, default=40, help='untimed simulated days before the warm-up')
+    ap.add_argument('--seed-fraction', type=float, default=0.002)
+    ap.add_argument('--cpu-agents', type=int, default=1_500_000, help='agents of the bounded CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_replica(args):
+    """One oracle replica: `days` simulated days after `warm` warm-up days; returns seconds."""
+    n_agents, districts, seed_fraction, warm, days, member = args
+    from abm_b200 import synth, tables
+    from oracle.abm_oracle import OracleModel
+    spec = synth.make_spec(n_districts=districts, R0=1.9, seed=POP_SEED)
+    pop = synth.make_population(n_agents, spec, seed=POP_SEED)
+    seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(seed_fraction * n_agents)), seed=POP_SEED + member)
+    ora = OracleModel(pop, dict(od_cum=spec.od_cum, mild_prob=1.0), tables.build_tables(spec), 1000 + member)
+    ora.set_epidemic_status(seeds)
+    for _ in range(warm * SUBSTEPS_PER_DAY):
+        ora.step()
+    t0 = time.perf_counter()
+    for _ in range(days * SUBSTEPS_PER_DAY):
+        ora.step()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_sample(n_agents, districts, seed_fraction, days=2, warm=1):
+    """Oracle port (numpy restatement of the reference step) on ONE host core, bounded sample."""
+    secs = _cpu_replica((n_agents, districts, seed_fraction, warm, days, 0))
+    return dict(value=n_agents * days / secs, unit=UNIT, cores=1, kind='port',
+                sample=f'{n_agents} agents x {days} days after {warm} warm-up day(s), {districts} districts, numpy oracle '
+                       f'(oracle/abm_oracle.py), {secs:.1f} s')
+
+
+def run_reference_arm(a):
+    """--impl reference: the CPU implementation on all host cores, the way the reference uses a multi-core box:
+    P independent single-threaded replicas (scripts/run_simulation_scenarios_full_data.py:30,41-46)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    n = a.cpu_agents
+    warm = min(a.warmup, 1)
+    days = max(1, min(a.steps, 3))
+    t0 = time.perf_counter()
+    with mp.get_context('spawn').Pool(procs) as pool:
+        secs = pool.map(_cpu_replica, [(n, a.districts, a.seed_fraction, warm, days, m) for m in range(procs)])
+    wall = max(secs)
+    value = procs * n * days / wall
+    sample = (f'{procs} independent replicas x {n} agents x {days} days ({warm} warm-up), numpy oracle port of the '
+              f'reference step; slowest replica {wall:.1f} s; whole arm {time.perf_counter() - t0:.1f} s')
+    line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=days, warmup=warm,
+                ms_per_step=wall / days * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='int64',
+                data='synthetic',
+                config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.districts} districts, unmitigated R0=1.9, '
+                                     '4 h sub-steps', agents_per_replica=n, replicas=procs),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind='port', sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda_arm(a):
+    import torch
+    from abm_b200 import distributed, sharding, synth, tables
+    from abm_b200.engine import Simulation, load_library
+    import __graft_entry__ as entry
+
+    rank, world, local = distributed.init_from_env()
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        torch.distributed.barrier()
+    lib = load_library()
+    device = torch.device('cuda', local)
+    torch.cuda.set_device(device)
+    n_total = a.agents_per_gpu * world
+    spec = synth.make_spec(n_districts=a.districts, R0=1.9, seed=POP_SEED)
+    tab = tables.build_tables(spec)
+    pop, base, dstart = sharding.make_synthetic_shard(n_total, spec, POP_SEED, world, rank)
+    uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None
+    local_seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=POP_SEED + rank) + base
+
+    def make_sim():
+        sim = Simulation(spec, pop, seed=POP_SEED, device=local, tables=tab, max_days=a.spinup + a.warmup + a.steps + 8,
+                         agent_id_base=base, district_start=dstart, world_size=world, rank=rank, nccl_unique_id=uid)
+        sim.seed_infections(local_seeds)
+        return sim
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    sim = make_sim()
+    sim.step(a.spinup * SUBSTEPS_PER_DAY)
+    for _ in range(a.warmup):
+        sim.step(SUBSTEPS_PER_DAY)
+    barrier()
+    launches0 = sim.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(a.steps):
+            sim.step(SUBSTEPS_PER_DAY)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_total * a.steps / (ms / 1e3)
+    prevalence = sim.counters()
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream (live, same state)
+    sim.set_profiling(True)
+    prof_days = max(1, min(a.steps, 5))
+    sim.step(prof_days * SUBSTEPS_PER_DAY)
+    kms, klaunches = sim.kernel_time()
+    sim.set_profiling(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    per_launch_bytes = ALGO_BYTES_PER_AGENT_DAY / SUBSTEPS_PER_DAY * pop.n
+    achieved = per_launch_bytes / (kms / klaunches * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'dram_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('bytes_per_launch')
+        except Exception:
+            traffic = None
+    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
+                    kernel='abm_substep_kernel', avg_launch_ms=kms / klaunches, launches_timed=klaunches,
+                    algorithmic_bytes_per_launch=per_launch_bytes,
+                    peak_source='MEASURED_PEAKS.json (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                    own_layout_bytes_per_launch=8.0 * sim.sm.n_slots)
+
+    # ---- end to end through the public API with host buffers: upload the agent store from pinned host memory,
+    #      run the same K days reading each day's log row back, download the final state word
+    e2e = None
+    if not a.no_e2e:
+        sim.close()
+        del sim
+        torch.cuda.synchronize(device)
+        barrier()
+        t0 = time.perf_counter()
+        sim = make_sim()                      # host -> device copies of every per-agent vector + tables
+        h2d = sum(v.numel() * v.element_size() for v in sim.buf.values())
+        d2h = 0
+        for _ in range(a.steps):
+            sim.step(SUBSTEPS_PER_DAY)
+            rows = sim.read_log()             # device -> host read of the day's counters (synchronises)
+            d2h += 16 * 8
+        flags = sim.buf['flags'].cpu()        # final packed state
+        d2h += flags.numel() * flags.element_size()
+        barrier()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
+        wall = float(tw.item())
+        e2e = dict(value=n_total * a.steps / wall, unit=UNIT, h2d_bytes_per_step=h2d / a.steps,
+                   d2h_bytes_per_step=d2h / a.steps, seconds=wall,
+                   note='includes slot-map build, pinned upload of the whole agent store, seeding, K days with a log '
+                        'read-back per day, and the final state download (early-epidemic days: cheaper kernels)')
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline_sample(a.cpu_agents, a.districts, a.seed_fraction)
+
+    if rank == 0:
+        hot_mb = 8.0 * sim.sm.n_slots / 1e6
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps,
+            higher_is_better=True, scaling='weak', vs_baseline=None, dtype='u32/int64', data='synthetic',
+            config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.agents_per_gpu} agents per GPU x {world} GPU(s), '
+                                 f'{a.districts} districts, unmitigated R0=1.9, 4 h sub-steps (6 per simulated day), '
+                                 f'household-aligned shards, NCCL all-reduce of the district x status tables per sub-step',
+                        agents_total=n_total, spinup_days=a.spinup, seed_fraction=a.seed_fraction,
+                        l2=f'per-GPU inputs {h2d / 1e6 if not a.no_e2e else 34.0 * pop.n / 1e6:.0f} MB > 126 MB L2; the 8 B/agent hot record swept '
+                           f'every sub-step is {hot_mb:.0f} MB (no explicit flush: re-sweeping it is the workload)',
+                        state_at_timing={k: prevalence[k] for k in ('current_exposed_cases', 'current_contagious_cases',
+                                                                    'infected_count', 'recovered_count')}),
+            roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks.summary())
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)

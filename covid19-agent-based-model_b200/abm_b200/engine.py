@@ -52,7 +52,7 @@ class AbmAgentPtrs(ct.Structure):
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
            'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
            'abm_kernel_time', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
-           'abm_version']
+           'abm_version', 'abm_nccl_unique_id']
 
 _lib = None
 
@@ -91,6 +91,7 @@ def load_library(path=LIB_PATH):
     lib.abm_last_error.restype = ct.c_char_p
     lib.abm_destroy.argtypes = [vp]
     lib.abm_destroy.restype = None
+    lib.abm_nccl_unique_id.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -128,7 +129,8 @@ class Simulation:
         n_slots = sm.n_slots
 
         def dev(a):
-            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            # page-locked staging + asynchronous copy on the current stream
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(self.device, non_blocking=True)
 
         def slots_from_agents(values, fill, dtype):
             out = np.full(n_slots, fill, dtype=dtype)

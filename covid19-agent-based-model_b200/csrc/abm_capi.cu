@@ -155,6 +155,20 @@ extern "C" {
 
 int abm_version(void) { return 100; }
 
+int abm_nccl_unique_id(void* out128) {
+    if (!out128) return ABM_ERR_ARG;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return ABM_ERR_NCCL;
+    typedef ncclResult_t (*get_id_fn)(ncclUniqueId*);
+    get_id_fn get_id = (get_id_fn)dlsym(lib, "ncclGetUniqueId");
+    if (!get_id) return ABM_ERR_NCCL;
+    ncclUniqueId id;
+    if (get_id(&id) != ncclSuccess) return ABM_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, sizeof id);
+    return ABM_OK;
+}
+
 const char* abm_last_error(abm_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int abm_create(const abm_config* cfg, abm_handle** out) {

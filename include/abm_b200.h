@@ -154,6 +154,8 @@ int abm_sync(abm_handle* h);
 const char* abm_last_error(abm_handle* h);
 void abm_destroy(abm_handle* h);
 int abm_version(void);
+/* ncclGetUniqueId into a 128-byte buffer (rank 0 calls it and broadcasts the bytes out of band). */
+int abm_nccl_unique_id(void* out128);
 
 #ifdef __cplusplus
 }
