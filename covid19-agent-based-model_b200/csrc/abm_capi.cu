@@ -181,14 +181,13 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if (cfg->n_status < 1 || cfg->n_status > ABM_MAX_STATUS) return fail(h, ABM_ERR_ARG, "n_status must be 1..%d", ABM_MAX_STATUS);
     if (cfg->n_districts < 1 || cfg->n_districts > 65535 || cfg->n_pools < cfg->n_districts) return fail(h, ABM_ERR_ARG, "bad district / pool count");
     if (cfg->hw_rows != 1 && cfg->hw_rows != cfg->n_districts) return fail(h, ABM_ERR_ARG, "hw_rows must be 1 or n_districts");
-    if (cfg->step_ticks <= 0 || cfg->max_log_rows < 1) return fail(h, ABM_ERR_ARG, "bad step_ticks / max_log_rows");
+    if (cfg->step_ticks < 2 || cfg->max_log_rows < 1) return fail(h, ABM_ERR_ARG, "bad step_ticks / max_log_rows");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return fail(h, ABM_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
     CUDA_TRY(h, cudaSetDevice(cfg->device));
-    if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
-    else { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    h->stream = (cudaStream_t)cfg->stream;   // NULL is the legacy default stream, which is also torch's default
     const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
     int rc;
     if ((rc = alloc_zero(h, 2 * pa, &h->acc))) return rc;
@@ -244,6 +243,7 @@ int abm_set_tables(abm_handle* h, const abm_tables* t) {
     if ((rc = upload(h, t->big_start, (size_t)c.n_big_households + 1, &T.big_start))) return rc;
     T.D = c.n_districts; T.A = c.n_status; T.P = c.n_pools; T.hw_rows = c.hw_rows; T.n_big = c.n_big_households;
     T.step_ticks = c.step_ticks; T.mild_active = c.mild_active;
+    T.step_inv = ~0ull / (unsigned long long)c.step_ticks + 1ull;   // floor(2^64 / step) + 1 for step >= 2 not a power of two; exact use in fire_index
     T.seed_lo = (uint32_t)c.seed; T.seed_hi = (uint32_t)(c.seed >> 32);
     T.symptomatic_rate = c.symptomatic_rate; T.critical_fatality_rate = c.critical_fatality_rate;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // host staging buffers may be released by the caller

@@ -58,6 +58,7 @@ struct DevTables {
     const uint16_t* tile_home; const int64_t* big_start;
     int32_t D, A, P, hw_rows, n_big, step_ticks, mild_active;
     uint32_t seed_lo, seed_hi;
+    unsigned long long step_inv;    // floor(2^64 / step_ticks) + 1
     double symptomatic_rate, critical_fatality_rate;
 };
 
@@ -123,28 +124,34 @@ __device__ __forceinline__ uint32_t sample_quantile_u32(const uint32_t* __restri
 }
 
 // 1 - exp(-x), x >= 0: fixed sequence of IEEE double ops (oracle.one_minus_exp_neg).
+template <int N>
 __device__ __forceinline__ double horner_omexp(double y) {
     double s = 1.0;
 #pragma unroll
-    for (int n = 20; n > 1; --n) s = __dsub_rn(1.0, __dmul_rn(__dmul_rn(y, 1.0 / (double)n), s));
+    for (int n = N; n > 1; --n) s = __dsub_rn(1.0, __dmul_rn(__dmul_rn(y, 1.0 / (double)n), s));
     return __dmul_rn(y, s);
 }
+// Taylor order by range: 9 terms below 2^-5, 13 below 2^-2, 20 below 2^-1 (all to < 1 ulp of the series)
 __device__ __forceinline__ double one_minus_exp_neg(double x) {
     x = fmin(x, 40.0);
-    if (x < 0.5) return horner_omexp(x);
-    double e = __dsub_rn(1.0, horner_omexp(__dmul_rn(x, 0.015625)));
+    if (x < 0.03125) return horner_omexp<9>(x);
+    if (x < 0.25) return horner_omexp<13>(x);
+    if (x < 0.5) return horner_omexp<20>(x);
+    double e = __dsub_rn(1.0, horner_omexp<20>(__dmul_rn(x, 0.015625)));
 #pragma unroll
     for (int i = 0; i < 6; ++i) e = __dmul_rn(e, e);
     return __dsub_rn(1.0, e);
 }
-__device__ __forceinline__ uint32_t hazard_threshold(double x) {
+__device__ __noinline__ uint32_t hazard_threshold(double x) {
     return (uint32_t)ceil(__dmul_rn(one_minus_exp_neg(x), 2147483648.0));
 }
 
-__device__ __forceinline__ uint32_t fire_index(int32_t t, int32_t step_ticks) {
+// sub-step index at which `date < now` first holds: floor(t / step) + 1, by multiply-high with
+// inv = floor(2^64 / step) + 1 (exact for every 32-bit t)
+__device__ __forceinline__ uint32_t fire_index(int32_t t, unsigned long long step_inv) {
     if (t == T_NEVER) return FIRE_NEVER;
     if (t < 0) return 0;
-    const uint32_t f = (uint32_t)(t / step_ticks) + 1u;
+    const uint32_t f = (uint32_t)__umul64hi((unsigned long long)(uint32_t)t, step_inv) + 1u;
     return f < 0xFFFEu ? f : 0xFFFEu;
 }
 
@@ -157,8 +164,11 @@ __device__ __forceinline__ uint32_t district_of(const DevTables& T, int64_t cid)
     }
     return (uint32_t)lo;
 }
-__device__ __forceinline__ uint32_t home_district(const DevTables& T, uint32_t f, uint32_t a, int64_t cid) {
-    return (f & F_AWAY) ? district_of(T, cid) : (a >> 16);
+// `tile_home` = home district of the tile's first agent: almost always the answer for an away agent
+__device__ __forceinline__ uint32_t home_district(const DevTables& T, uint32_t f, uint32_t a, int64_t cid, int tile_home = -1) {
+    if (!(f & F_AWAY)) return a >> 16;
+    if (tile_home >= 0 && cid < __ldg(T.district_start + tile_home + 1)) return (uint32_t)tile_home;
+    return district_of(T, cid);
 }
 __device__ __forceinline__ int big_slot(const DevTables& T, int64_t cid) {
     int lo = 0, hi = T.n_big;       // big_start[lo] <= cid < big_start[hi]
@@ -177,11 +187,12 @@ __device__ __forceinline__ bool at_own_household(uint32_t f) {
 // Outside pool (row of the district x status tables) the agent is currently in, or -1.
 // Hospital is location -current_district (base_model.py:270-272): district 0 maps onto its own outside
 // pool (quirk Q3); every other hospital / the dead location holds no susceptible agent.
-__device__ __forceinline__ int pool_of(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int64_t cid) {
+__device__ __forceinline__ int pool_of(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int64_t cid,
+                                       int tile_home = -1) {
     const uint32_t kind = (f >> F_LOC_SHIFT) & F_LOC_MASK;
     if (kind == LOC_ECON) {
         const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
-        if (ek == EKIND_HOME_DISTRICT) return (int)home_district(T, f, a, cid);
+        if (ek == EKIND_HOME_DISTRICT) return (int)home_district(T, f, a, cid, tile_home);
         if (ek == EKIND_POOL) return (int)__ldg(G.econ_pool + slot);
         return -1;
     }
@@ -233,8 +244,8 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
     f &= ~(F_EPI_MASK | (F_SYM_MASK << F_SYM_SHIFT) | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
     f |= EPI_I | ((sym ? 2u : 1u) << F_SYM_SHIFT) | out;                                    // :850
     // earliest scheduled event (contagious always precedes the others except when onset < 12 h)
-    uint32_t fi = fire_index(t_c, T.step_ticks);
-    const uint32_t fo = fire_index(t_o, T.step_ticks), fr = fire_index(t_r, T.step_ticks);
+    uint32_t fi = fire_index(t_c, T.step_inv);
+    const uint32_t fo = fire_index(t_o, T.step_inv), fr = fire_index(t_r, T.step_inv);
     fi = fi < fo ? fi : fo;
     fi = fi < fr ? fi : fr;
     fi = fi > k_first ? fi : k_first;
@@ -273,7 +284,7 @@ __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const D
     const int32_t ts[6] = {t_c, t_o, t_h, t_cs, t_d, t_r};
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-        if (ts[i] >= now) { const uint32_t x = fire_index(ts[i], T.step_ticks); nf = x < nf ? x : nf; }
+        if (ts[i] >= now) { const uint32_t x = fire_index(ts[i], T.step_inv); nf = x < nf ? x : nf; }
     a = (a & 0xFFFF0000u) | nf;
     return f;
 }
@@ -287,7 +298,7 @@ __device__ __forceinline__ bool is_active(uint32_t f, uint32_t a) {
 
 // go_out for one active agent (base_model.py:304-441).
 __device__ __forceinline__ uint32_t go_out_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                 int64_t cid, const StepArgs& s) {
+                                                 int64_t cid, const StepArgs& s, int tile_home) {
     const bool weekday = (s.mode & M_WEEKDAY) != 0;                                         // :309-312
     const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;           // :212-219, :316
     const uint32_t thr = __ldg(T.move_thr + 4 * (uint32_t)__ldg(G.move_class + slot) + (weekday ? 0 : 2) + (mild ? 1 : 0));
@@ -297,11 +308,9 @@ __device__ __forceinline__ uint32_t go_out_agent(const DevTables& T, const DevAg
     U4 X = U4{0, 0, 0, 0};
     if (thr < 0x80000000u || needs_od) X = agent_draws(T, cid, s.k, 0u);
     if (!((X.y >> 1) < thr)) return f;                                                      // :317-318 not a mover
-    bool returning = false;
     if (away && G.t_return[slot] < s.now) {                                                 // :342-360
-        returning = true;
+        a = (a & 0xFFFFu) | (home_district(T, f, a, cid, tile_home) << 16);
         f &= ~F_AWAY;
-        a = (a & 0xFFFFu) | (district_of(T, cid) << 16);
     }
     bool left = false;
     if (needs_od && !(f & F_AWAY)) {                                                        // :366-370
@@ -341,201 +350,189 @@ __device__ __forceinline__ uint32_t go_out_agent(const DevTables& T, const DevAg
         }
     }
     if (!left) f = (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_ECON << F_LOC_SHIFT);           // :331-339, :346-352
-    (void)returning;
     return f;
 }
 
 // go_home for one active agent (base_model.py:274-302).
 __device__ __forceinline__ uint32_t go_home_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                  int64_t cid, const StepArgs& s) {
+                                                  int64_t cid, const StepArgs& s, int tile_home) {
     if (!(f & F_AWAY)) return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
     if (G.t_return[slot] < s.now) {
+        a = (a & 0xFFFFu) | (home_district(T, f, a, cid, tile_home) << 16);
         f &= ~F_AWAY;
-        a = (a & 0xFFFFu) | (district_of(T, cid) << 16);
         return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
     }
     return f;
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
+// One block = one tile of 1024 slots; one thread = 4 consecutive slots (one 128-bit load of each hot word).
+// The per-agent work runs in a NON-unrolled loop that rotates the four register pairs, so every inlined
+// path exists once in the instruction stream (the unrolled form overflowed the instruction cache).
 __global__ void __launch_bounds__(THREADS, 4)
 abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
-    __shared__ uint16_t s_code[ABM_TILE];          // household walk: bit15 head, bit14 contagious at home, low 8 sym|age
+    __shared__ uint16_t s_code[ABM_TILE];   // bit15 household head, bit14 contagious at home, low 8 bits sym|age
+    __shared__ uint32_t s_thr[ABM_TILE];    // household infection threshold of every slot (0 = no exposure)
     __shared__ unsigned int s_tally[N_TALLY];
     __shared__ unsigned int s_cnt[ABM_MAX_STATUS];
-    __shared__ unsigned long long s_r[ABM_MAX_STATUS];
+    __shared__ unsigned int s_rlo[ABM_MAX_STATUS], s_rhi[ABM_MAX_STATUS];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t tile = blockIdx.x;
     const int64_t slot0 = tile * ABM_TILE + (int64_t)tid * PER_THREAD;
-    const int64_t tbase = __ldg(T.tile_base + tile);
-    const int tcount = (int)(__ldg(T.tile_base + tile + 1) - tbase);
-    const int64_t cid0 = tbase + (int64_t)tid * PER_THREAD;
-
-    if (tid < N_TALLY) s_tally[tid] = 0;
-    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_r[tid] = 0ull; }
+    const int64_t cid0 = __ldg(T.tile_base + tile) + (int64_t)tid * PER_THREAD;
+    const int L0 = (int)__ldg(T.tile_home + tile);
 
     const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
     const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
-    uint32_t f[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
-    uint32_t a[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
-    const uint32_t f_in[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
-    const uint32_t a_in[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
+    uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
+    uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
 
-    // ---------------------------------------------------------------- I(k-1): infection draw
+    if (tid < N_TALLY) s_tally[tid] = 0;
+    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_rlo[tid] = 0; s_rhi[tid] = 0; }
+
+    // ---------------------------------------------------------------- household thresholds for I(k-1)
+    int tile_has_cont_home = 0;
     if (s.mode & M_INFECT) {
+        const uint32_t fs[PER_THREAD] = {f0, f1, f2, f3};
+        uint32_t code[PER_THREAD];
         bool any_cont_home = false;
-        uint16_t code[PER_THREAD];
 #pragma unroll
         for (int j = 0; j < PER_THREAD; ++j) {
-            const uint32_t fj = f[j];
+            const uint32_t fj = fs[j];
             const bool ch = (fj & F_EPI_MASK) == EPI_C && at_own_household(fj) && !(fj & F_BIGHH);
             any_cont_home |= ch;
-            code[j] = (uint16_t)(((fj & F_HEAD) ? 0x8000u : 0u) | (ch ? 0x4000u : 0u) |
-                                 ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 0x80u : 0u) | ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+            code[j] = ((fj & F_HEAD) ? 0x8000u : 0u) | (ch ? 0x4000u : 0u) | ((fj & (F_BIGHH | F_FILLER)) ? 0x2000u : 0u) |
+                      ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 0x80u : 0u) | ((fj >> F_AGE_SHIFT) & F_AGE_MASK);
         }
-        const int tile_has_cont_home = __syncthreads_or(any_cont_home);
+        *reinterpret_cast<uint2*>(s_code + tid * PER_THREAD) = make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
+        *reinterpret_cast<uint4*>(s_thr + tid * PER_THREAD) = make_uint4(0u, 0u, 0u, 0u);
+        tile_has_cont_home = __syncthreads_or(any_cont_home);
         if (tile_has_cont_home) {
-            *reinterpret_cast<uint2*>(s_code + tid * PER_THREAD) =
-                make_uint2((uint32_t)code[0] | ((uint32_t)code[1] << 16), (uint32_t)code[2] | ((uint32_t)code[3] << 16));
-            __syncthreads();
-        }
-        unsigned long long hsum = 0ull;
-        bool hvalid = false;
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            uint32_t fj = f[j];
-            if (fj & F_HEAD) hvalid = false;
-            if ((fj & F_EPI_MASK) != EPI_S) continue;
-            const int64_t slot = slot0 + j, cid = cid0 + j;
-            uint32_t thr = 0;
-            if (at_own_household(fj)) {
-                unsigned long long hz = 0ull;
-                if (fj & F_BIGHH) {
-                    hz = Wk.hbig_read[big_slot(T, cid)];
-                } else if (tile_has_cont_home) {
-                    if (!hvalid) {
-                        int o = tid * PER_THREAD + j;
-                        int b = o;
-                        while (b > 0 && !(s_code[b] & 0x8000u)) --b;
-                        const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, a[j], cid) : 0u;
-                        const uint32_t* q = T.qfx + (size_t)qrow * 256;
-                        hsum = 0ull;
-                        int e = b;
-                        do {
-                            const uint32_t c = s_code[e];
-                            if (c & 0x4000u) hsum += __ldg(q + (c & 0xFFu));
-                            ++e;
-                        } while (e < ABM_TILE && !(s_code[e] & 0x8000u));
-                        hvalid = true;
-                        (void)o;
+            // every household head sums its members' log-survival increments and publishes the threshold
+#pragma unroll 1
+            for (int j = 0; j < PER_THREAD; ++j) {
+                const int o = tid * PER_THREAD + j;
+                uint32_t c = s_code[o];
+                if ((c & 0xA000u) != 0x8000u) continue;      // not a head, or big household / filler
+                int e = o;
+                unsigned long long hsum = 0ull;
+                const uint32_t* q = T.qfx;
+                bool have_q = false;
+                do {
+                    if (c & 0x4000u) {
+                        if (!have_q) {
+                            if (T.hw_rows > 1) q += (size_t)home_district(T, G.flags[slot0 + j], G.aux[slot0 + j], cid0 + j, L0) * 256;
+                            have_q = true;
+                        }
+                        hsum += __ldg(q + (c & 0xFFu));
                     }
-                    hz = hsum;
-                }
-                if (hz) thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0));
-            } else {
-                const int pool = pool_of(T, G, fj, a[j], slot, cid);
-                if (pool >= 0) thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
-            }
-            if (thr) {
-                const U4 X = agent_draws(T, cid, s.k_inf, 0u);
-                if ((X.x >> 1) < thr) {
-                    f[j] = infect_agent(T, G, fj, a[j], slot, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
-                    atomicAdd(s_tally + CUM_INFECTED, 1u);
+                    ++e;
+                    if (e >= ABM_TILE) break;
+                    c = s_code[e];
+                } while (!(c & 0x8000u));
+                if (hsum) {
+                    const uint32_t thr = hazard_threshold(__dmul_rn((double)hsum, 1.0 / 4294967296.0));
+                    for (int m = o; m < e; ++m) s_thr[m] = thr;
                 }
             }
+            __syncthreads();
         }
     } else {
         __syncthreads();   // s_tally / s_cnt initialisation
     }
 
-    if (s.mode & M_STEP) {
-        // ------------------------------------------------------------ log: "current" counters before T(k)
-        if (s.mode & M_LOG) {
-            uint32_t c = 0;   // 4 x 8-bit packed counts (<= 4 each)
-#pragma unroll
-            for (int j = 0; j < PER_THREAD; ++j) {
-                const uint32_t epi = f[j] & F_EPI_MASK, clin = (f[j] >> F_CLIN_SHIFT) & F_CLIN_MASK;
-                c += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+    uint32_t cw0 = 0, cw1 = 0, cw2 = 0;    // packed per-status head counts of this thread (8 bits each)
+    uint32_t logc = 0;                     // packed "current" counters for the day log
+    bool changed_f = false, changed_a = false;
+
+#pragma unroll 1
+    for (int j = 0; j < PER_THREAD; ++j) {
+        uint32_t fj = f0, aj = a0;
+        const int64_t slot = slot0 + j, cid = cid0 + j;
+        // ------------------------------------------------------------ I(k-1): infection draw
+        if ((s.mode & M_INFECT) && (fj & F_EPI_MASK) == EPI_S) {
+            uint32_t thr = 0;
+            if (at_own_household(fj)) {
+                if (fj & F_BIGHH) {
+                    const unsigned long long hz = Wk.hbig_read[big_slot(T, cid)];
+                    if (hz) thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0));
+                } else if (tile_has_cont_home) {
+                    thr = s_thr[tid * PER_THREAD + j];
+                }
+            } else {
+                const int pool = pool_of(T, G, fj, aj, slot, cid, L0);
+                if (pool >= 0) thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
             }
-            c = __reduce_add_sync(0xFFFFFFFFu, c);   // <= 128 per field
+            if (thr) {
+                const U4 X = agent_draws(T, cid, s.k_inf, 0u);
+                if ((X.x >> 1) < thr) {
+                    fj = infect_agent(T, G, fj, aj, slot, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+                    atomicAdd(s_tally + CUM_INFECTED, 1u);
+                }
+            }
+        }
+        if (s.mode & M_STEP) {
+            // -------------------------------------------------------- log: "current" counters before T(k)
+            if (s.mode & M_LOG) {
+                const uint32_t epi = fj & F_EPI_MASK, clin = (fj >> F_CLIN_SHIFT) & F_CLIN_MASK;
+                logc += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+            }
+            // -------------------------------------------------------- T(k) transitions, M(k) movement
+            if ((aj & 0xFFFFu) <= (uint32_t)s.k) fj = transition_agent(T, G, fj, aj, slot, s.now, s_tally);
+            if ((s.mode & (M_GO_OUT | M_GO_HOME)) && !(fj & F_FILLER) && is_active(fj, aj)) {
+                if (s.mode & M_GO_HOME) fj = go_home_agent(T, G, fj, aj, slot, cid, s, L0);
+                if (s.mode & M_GO_OUT) fj = go_out_agent(T, G, fj, aj, slot, cid, s, L0);
+            }
+            // -------------------------------------------------------- A(k): pressure / headcount tables
+            const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
+            const int pool = pool_of(T, G, fj, aj, slot, cid, L0);
+            const bool cont = (fj & F_EPI_MASK) == EPI_C;
+            if (pool >= 0) {
+                const uint32_t r = cont ? __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK)) : 0u;
+                if (pool == L0) {
+                    const uint32_t inc = 1u << (8 * (st & 3));
+                    if ((st >> 2) == 0) cw0 += inc; else if ((st >> 2) == 1) cw1 += inc; else cw2 += inc;
+                    if (cont) { atomicAdd(s_rlo + st, r & 0xFFFFu); atomicAdd(s_rhi + st, r >> 16); }
+                } else {
+                    atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)pool * T.A + st, 1ull);
+                    if (cont) atomicAdd(Wk.acc + (size_t)pool * T.A + st, (unsigned long long)r);
+                }
+            } else if (cont && (fj & F_BIGHH) && at_own_household(fj)) {
+                const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, aj, cid, L0) : 0u;
+                const uint32_t q = __ldg(T.qfx + (size_t)qrow * 256 + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
+                atomicAdd(Wk.hbig_write + big_slot(T, cid), (unsigned long long)q);
+            }
+        }
+        changed_f |= fj != f0;
+        changed_a |= aj != a0;
+        // rotate the register file: slot j+1 becomes the current one, the processed one goes to the back
+        f0 = f1; f1 = f2; f2 = f3; f3 = fj;
+        a0 = a1; a1 = a2; a2 = a3; a3 = aj;
+    }
+
+    // ---------------------------------------------------------------- write back what changed
+    if (changed_f) *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
+    if (changed_a) *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
+
+    if (s.mode & M_STEP) {
+        if (s.mode & M_LOG) {
+            logc = __reduce_add_sync(0xFFFFFFFFu, logc);   // <= 128 per 8-bit field
             if (lane < 4) {
-                const unsigned int v = (c >> (8 * lane)) & 0xFFu;
+                const unsigned int v = (logc >> (8 * lane)) & 0xFFu;
                 if (v) atomicAdd(s_tally + CUR_EXPOSED + lane, v);
             }
         }
-        // ------------------------------------------------------------ T(k) transitions, M(k) movement
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const int64_t slot = slot0 + j, cid = cid0 + j;
-            if ((a[j] & 0xFFFFu) <= (uint32_t)s.k) f[j] = transition_agent(T, G, f[j], a[j], slot, s.now, s_tally);
-            if ((s.mode & (M_GO_OUT | M_GO_HOME)) && !(f[j] & F_FILLER) && is_active(f[j], a[j])) {
-                if (s.mode & M_GO_HOME) f[j] = go_home_agent(T, G, f[j], a[j], slot, cid, s);
-                if (s.mode & M_GO_OUT) f[j] = go_out_agent(T, G, f[j], a[j], slot, cid, s);
-            }
-        }
-        // ------------------------------------------------------------ A(k): pressure / headcount tables
-        const int L0 = (int)__ldg(T.tile_home + tile);
-        uint32_t cw[3] = {0, 0, 0};
-        int pool[PER_THREAD];
-        bool cont_any = false;
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const uint32_t fj = f[j];
-            const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
-            pool[j] = pool_of(T, G, fj, a[j], slot0 + j, cid0 + j);
-            const bool cont = (fj & F_EPI_MASK) == EPI_C;
-            if (pool[j] == L0) {
-                const uint32_t inc = 1u << (8 * (st & 3));
-                if ((st >> 2) == 0) cw[0] += inc; else if ((st >> 2) == 1) cw[1] += inc; else cw[2] += inc;
-                cont_any |= cont;
-            } else if (pool[j] >= 0) {
-                atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)pool[j] * T.A + st, 1ull);
-                if (cont) {
-                    const uint32_t r = __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
-                    atomicAdd(Wk.acc + (size_t)pool[j] * T.A + st, (unsigned long long)r);
-                }
-            }
-            if (cont && (fj & F_BIGHH) && at_own_household(fj)) {
-                const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, a[j], cid0 + j) : 0u;
-                const uint32_t q = __ldg(T.qfx + (size_t)qrow * 256 + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
-                atomicAdd(Wk.hbig_write + big_slot(T, cid0 + j), (unsigned long long)q);
-            }
-        }
         // head counts: 3 packed warp reductions, lane b keeps status b
-        const uint32_t w0 = __reduce_add_sync(0xFFFFFFFFu, cw[0]);
-        const uint32_t w1 = __reduce_add_sync(0xFFFFFFFFu, cw[1]);
-        const uint32_t w2 = __reduce_add_sync(0xFFFFFFFFu, cw[2]);
+        const uint32_t w0 = __reduce_add_sync(0xFFFFFFFFu, cw0);
+        const uint32_t w1 = __reduce_add_sync(0xFFFFFFFFu, cw1);
+        const uint32_t w2 = __reduce_add_sync(0xFFFFFFFFu, cw2);
         if (lane < T.A) {
             const uint32_t w = (lane >> 2) == 0 ? w0 : ((lane >> 2) == 1 ? w1 : w2);
             const unsigned int v = (w >> (8 * (lane & 3))) & 0xFFu;
             if (v) atomicAdd(s_cnt + lane, v);
         }
-        // infectious pressure: only warps that hold a contagious agent in the tile's home pool
-        if (__any_sync(0xFFFFFFFFu, cont_any)) {
-            for (int b = 0; b < T.A; ++b) {
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int j = 0; j < PER_THREAD; ++j) {
-                    const uint32_t fj = f[j];
-                    if (pool[j] == L0 && (fj & F_EPI_MASK) == EPI_C && (int)((fj >> F_STATUS_SHIFT) & F_STATUS_MASK) == b) {
-                        const uint32_t r = __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
-                        lo += r & 0xFFFFu; hi += r >> 16;
-                    }
-                }
-                lo = __reduce_add_sync(0xFFFFFFFFu, lo);
-                hi = __reduce_add_sync(0xFFFFFFFFu, hi);
-                if (lane == 0 && (lo | hi)) atomicAdd(s_r + b, ((unsigned long long)hi << 16) + lo);
-            }
-        }
     }
-
-    // ---------------------------------------------------------------- write back what changed
-    if (f[0] != f_in[0] || f[1] != f_in[1] || f[2] != f_in[2] || f[3] != f_in[3])
-        *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f[0], f[1], f[2], f[3]);
-    if (a[0] != a_in[0] || a[1] != a_in[1] || a[2] != a_in[2] || a[3] != a_in[3])
-        *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a[0], a[1], a[2], a[3]);
-
     __syncthreads();
     if (tid < N_TALLY) {
         const unsigned int v = s_tally[tid];
@@ -545,15 +542,12 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                            (unsigned long long)v);
         }
     }
-    if ((s.mode & M_STEP) && tid >= 32 && tid < 32 + ABM_MAX_STATUS) {
+    if ((s.mode & M_STEP) && tid >= 32 && tid < 32 + T.A) {
         const int b = tid - 32;
-        const int L0 = (int)__ldg(T.tile_home + tile);
-        if (b < T.A) {
-            if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)L0 * T.A + b, (unsigned long long)s_cnt[b]);
-            if (s_r[b]) atomicAdd(Wk.acc + (size_t)L0 * T.A + b, s_r[b]);
-        }
+        if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)L0 * T.A + b, (unsigned long long)s_cnt[b]);
+        const unsigned long long r = ((unsigned long long)s_rhi[b] << 16) + s_rlo[b];
+        if (r) atomicAdd(Wk.acc + (size_t)L0 * T.A + b, r);
     }
-    (void)tcount;
 }
 
 // ------------------------------------------------------------------------------------------------ table kernel

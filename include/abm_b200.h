@@ -76,7 +76,7 @@ typedef struct {
     uint64_t seed;              /* Philox key                                                       */
     double symptomatic_rate;    /* params.SYMPTOMATIC_RATE                                          */
     double critical_fatality_rate;
-    void* stream;               /* cudaStream_t to enqueue on (NULL = library-owned stream)         */
+    void* stream;               /* cudaStream_t to enqueue on (NULL = the legacy default stream)    */
     int32_t world_size;         /* ranks sharing the district tables (1 = no collective)            */
     int32_t rank;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1            */

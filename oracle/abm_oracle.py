@@ -67,20 +67,21 @@ def sample_quantile(table2, x):
 
 def one_minus_exp_neg(x):
     """1 - exp(-x) for x >= 0 by a fixed sequence of IEEE double multiplies/adds (no FMA):
-    Taylor-Horner below 0.5, six squarings of exp(-x/64) above.  Mirrored op for op in CUDA."""
+    Taylor-Horner of order 9 / 13 / 20 below 2^-5 / 2^-2 / 2^-1, six squarings of exp(-x/64) above.
+    Mirrored op for op in CUDA (abm_kernels.cuh one_minus_exp_neg)."""
     x = np.minimum(np.asarray(x, dtype=np.float64), HAZARD_CLAMP)
 
-    def horner(y):
+    def horner(y, terms):
         s = np.ones_like(y)
-        for n in range(HAZARD_TERMS, 1, -1):
+        for n in range(terms, 1, -1):
             s = 1.0 - (y * INV[n]) * s
         return y * s
 
-    small = horner(x)
-    e = 1.0 - horner(x * 0.015625)
+    e = 1.0 - horner(x * 0.015625, 20)
     for _ in range(6):
         e = e * e
-    return np.where(x < 0.5, small, 1.0 - e)
+    return np.where(x < 0.03125, horner(x, 9),
+                    np.where(x < 0.25, horner(x, 13), np.where(x < 0.5, horner(x, 20), 1.0 - e)))
 
 
 def hazard_threshold(x):
