@@ -129,7 +129,14 @@ int launch_main(abm_handle* h, const StepArgs& s, long long* log_row) {
         h->prof_used++;
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
-    abm_substep_kernel<<<(unsigned)h->cfg.n_tiles, THREADS, 0, h->stream>>>(h->T, h->G, w, s);
+    const dim3 grid((unsigned)h->cfg.n_tiles), block(THREADS);
+    const uint32_t m = s.mode & ~M_WEEKDAY;
+    // the four sub-step kinds of a simulated day get their own instantiation; anything else is generic
+    if (m == (M_INFECT | M_STEP)) abm_substep_kernel<M_INFECT | M_STEP><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
+    else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_LOG)) abm_substep_kernel<M_INFECT | M_STEP | M_GO_OUT | M_LOG><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
+    else if (m == (M_INFECT | M_STEP | M_GO_HOME)) abm_substep_kernel<M_INFECT | M_STEP | M_GO_HOME><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
+    else if (m == M_INFECT) abm_substep_kernel<M_INFECT><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
+    else abm_substep_kernel<RUNTIME_MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
     if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;

@@ -296,141 +296,114 @@ __device__ __forceinline__ bool is_active(uint32_t f, uint32_t a) {
     return (clin < 1 || epi == EPI_R) && loc_ok;
 }
 
-// go_out for one active agent (base_model.py:304-441).
-__device__ __forceinline__ uint32_t go_out_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                 int64_t cid, const StepArgs& s, int tile_home) {
-    const bool weekday = (s.mode & M_WEEKDAY) != 0;                                         // :309-312
-    const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;           // :212-219, :316
-    const uint32_t thr = __ldg(T.move_thr + 4 * (uint32_t)__ldg(G.move_class + slot) + (weekday ? 0 : 2) + (mild ? 1 : 0));
-    if (thr == 0) return f;
-    const bool away = (f & F_AWAY) != 0;
-    const bool needs_od = (f & F_DMOVER) != 0;
-    U4 X = U4{0, 0, 0, 0};
-    if (thr < 0x80000000u || needs_od) X = agent_draws(T, cid, s.k, 0u);
-    if (!((X.y >> 1) < thr)) return f;                                                      // :317-318 not a mover
-    if (away && G.t_return[slot] < s.now) {                                                 // :342-360
-        a = (a & 0xFFFFu) | (home_district(T, f, a, cid, tile_home) << 16);
-        f &= ~F_AWAY;
+// Length of stay for a traveller leaving `home` for `dest` on `weekday` (base_model.py:418-434): Gamma(mean^2/std,
+// std/mean) hours (params.py:576-580, quirk Q7) through the Wilson-Hilferty transform of a table normal draw.
+__device__ __forceinline__ int32_t stay_return_tick(const DevTables& T, uint32_t x3, int weekday, uint32_t home, uint32_t dest, int32_t now) {
+    const double* par = T.stay_par + (((size_t)weekday * T.D + home) * T.D + dest) * 3;
+    const uint32_t mag_x = x3 << 1;
+    const uint32_t i = mag_x >> 20, fr = mag_x & 0xFFFFFu;
+    int64_t mag;
+    if (i < ABM_QN - 1) {
+        const int64_t zl = __ldg(T.znorm + i), zh = __ldg(T.znorm + i + 1);
+        mag = zl + (((zh - zl) * (int64_t)fr) >> 20);
+    } else {
+        const uint32_t j = fr >> 8, g = fr & 0xFFu;
+        const int64_t zl = __ldg(T.znorm + (ABM_QN + 1) + j), zh = __ldg(T.znorm + (ABM_QN + 1) + j + 1);
+        mag = zl + (((zh - zl) * (int64_t)g) >> 8);
     }
-    bool left = false;
-    if (needs_od && !(f & F_AWAY)) {                                                        // :366-370
-        const uint32_t home = a >> 16;
-        const uint32_t* row = T.od_thr + ((size_t)s.weekday * T.D + home) * T.D;
-        const uint32_t u = X.z >> 1;
-        // first column j with u < thr[j] (rows are non-decreasing); none -> column 0 (quirk Q8)   :372-377
-        int lo = 0, hi = T.D;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (u < __ldg(row + mid)) hi = mid; else lo = mid + 1;
-        }
-        const uint32_t dest = lo < T.D ? (uint32_t)lo : 0u;
-        if (dest != home) {                                                                 // :410-439
-            const double* par = T.stay_par + (((size_t)s.weekday * T.D + home) * T.D + dest) * 3;
-            const uint32_t mag_x = X.w << 1;
-            const uint32_t i = mag_x >> 20, fr = mag_x & 0xFFFFFu;
-            int64_t mag;
-            if (i < ABM_QN - 1) {
-                const int64_t zl = __ldg(T.znorm + i), zh = __ldg(T.znorm + i + 1);
-                mag = zl + (((zh - zl) * (int64_t)fr) >> 20);
-            } else {
-                const uint32_t j = fr >> 8, g = fr & 0xFFu;
-                const int64_t zl = __ldg(T.znorm + (ABM_QN + 1) + j), zh = __ldg(T.znorm + (ABM_QN + 1) + j + 1);
-                mag = zl + (((zh - zl) * (int64_t)g) >> 8);
-            }
-            const double z = __dmul_rn((double)((X.w >> 31) ? -mag : mag), 1.0 / 65536.0);
-            const double t = __dadd_rn(__ldg(par + 1), __dmul_rn(__ldg(par + 2), z));
-            const double hours = __dmul_rn(__ldg(par + 0), __dmul_rn(__dmul_rn(t, t), t));
-            const double m = floor(fmin(fmax(__dmul_rn(hours, 60.0), 0.0), 1.0e9));
-            const int64_t ret = (int64_t)s.now + (int64_t)m;
-            G.t_return[slot] = (int32_t)(ret < (int64_t)T_NEVER - 1 ? ret : (int64_t)T_NEVER - 1);
-            f |= F_AWAY;
-            a = (a & 0xFFFFu) | (dest << 16);
-            f = (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_DIST << F_LOC_SHIFT);
-            left = true;
-        }
-    }
-    if (!left) f = (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_ECON << F_LOC_SHIFT);           // :331-339, :346-352
-    return f;
+    const double z = __dmul_rn((double)((x3 >> 31) ? -mag : mag), 1.0 / 65536.0);
+    const double t = __dadd_rn(__ldg(par + 1), __dmul_rn(__ldg(par + 2), z));
+    const double hours = __dmul_rn(__ldg(par + 0), __dmul_rn(__dmul_rn(t, t), t));
+    const double m = floor(fmin(fmax(__dmul_rn(hours, 60.0), 0.0), 1.0e9));
+    const int64_t ret = (int64_t)now + (int64_t)m;
+    return (int32_t)(ret < (int64_t)T_NEVER - 1 ? ret : (int64_t)T_NEVER - 1);
 }
 
-// go_home for one active agent (base_model.py:274-302).
-__device__ __forceinline__ uint32_t go_home_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                  int64_t cid, const StepArgs& s, int tile_home) {
-    if (!(f & F_AWAY)) return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
-    if (G.t_return[slot] < s.now) {
-        a = (a & 0xFFFFu) | (home_district(T, f, a, cid, tile_home) << 16);
-        f &= ~F_AWAY;
-        return (f & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
+// first column j with u < thr[j] of a non-decreasing OD row; none -> column 0 (quirk Q8)   base_model.py:372-377
+__device__ __forceinline__ uint32_t od_destination(const DevTables& T, uint32_t u, int weekday, uint32_t home) {
+    const uint32_t* row = T.od_thr + ((size_t)weekday * T.D + home) * T.D;
+    int lo = 0, hi = T.D;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u < __ldg(row + mid)) hi = mid; else lo = mid + 1;
     }
-    return f;
+    return lo < T.D ? (uint32_t)lo : 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
-// One block = one tile of 1024 slots; one thread = 4 consecutive slots (one 128-bit load of each hot word).
-// The per-agent work runs in a NON-unrolled loop that rotates the four register pairs, so every inlined
-// path exists once in the instruction stream (the unrolled form overflowed the instruction cache).
+// One block = one tile of 1024 slots staged in shared memory; one thread owns 4 consecutive slots (one
+// 128-bit load of each hot word).  Work that only a few agents need in a given sub-step (the infection
+// draw at night, the disease-course sampling, due transitions, length-of-stay sampling) is not executed
+// in place -- a warp would run it for one or two active lanes -- but appended to per-tile queues in
+// shared memory and then processed with all lanes busy.  MODE is the compile-time copy of StepArgs.mode
+// for the four sub-step kinds that make up a simulated day (RUNTIME_MODE = read it from the argument).
+constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
+constexpr int Q_DRAW = 0, Q_INFECT = 1, Q_TRANS = 2, Q_STAY = 3, N_QUEUES = 4;
+
+__device__ __forceinline__ void enqueue_one(unsigned int* s_n, uint16_t* s_q, int q, int o) {
+    const unsigned int pos = atomicAdd(s_n + q, 1u);
+    s_q[q * ABM_TILE + pos] = (uint16_t)o;
+}
+
+template <uint32_t MODE>
 __global__ void __launch_bounds__(THREADS, 4)
 abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
-    __shared__ uint16_t s_code[ABM_TILE];   // bit15 household head, bit14 contagious at home, low 8 bits sym|age
-    __shared__ uint32_t s_thr[ABM_TILE];    // household infection threshold of every slot (0 = no exposure)
+    __shared__ __align__(16) uint32_t s_f[ABM_TILE];     // staged flags
+    __shared__ __align__(16) uint32_t s_a[ABM_TILE];     // staged aux
+    __shared__ __align__(16) uint32_t s_thr[ABM_TILE];   // infection threshold per slot; later the stay draw
+    __shared__ uint16_t s_q[N_QUEUES * ABM_TILE];
+    __shared__ unsigned int s_n[N_QUEUES];
     __shared__ unsigned int s_tally[N_TALLY];
     __shared__ unsigned int s_cnt[ABM_MAX_STATUS];
     __shared__ unsigned int s_rlo[ABM_MAX_STATUS], s_rhi[ABM_MAX_STATUS];
 
+    const uint32_t mode = MODE == RUNTIME_MODE ? s.mode : ((MODE & ~M_WEEKDAY) | (s.mode & M_WEEKDAY));
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t tile = blockIdx.x;
-    const int64_t slot0 = tile * ABM_TILE + (int64_t)tid * PER_THREAD;
-    const int64_t cid0 = __ldg(T.tile_base + tile) + (int64_t)tid * PER_THREAD;
+    const int o0 = tid * PER_THREAD;
+    const int64_t slot0 = tile * ABM_TILE + o0;
+    const int64_t cid_tile = __ldg(T.tile_base + tile);
     const int L0 = (int)__ldg(T.tile_home + tile);
 
     const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
     const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
-    uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
-    uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
+    uint32_t f[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
+    uint32_t a[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
 
     if (tid < N_TALLY) s_tally[tid] = 0;
+    if (tid < N_QUEUES) s_n[tid] = 0;
     if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_rlo[tid] = 0; s_rhi[tid] = 0; }
+    *reinterpret_cast<uint4*>(s_f + o0) = f4;
+    *reinterpret_cast<uint4*>(s_a + o0) = a4;
+    *reinterpret_cast<uint4*>(s_thr + o0) = make_uint4(0u, 0u, 0u, 0u);
 
     // ---------------------------------------------------------------- household thresholds for I(k-1)
     int tile_has_cont_home = 0;
-    if (s.mode & M_INFECT) {
-        const uint32_t fs[PER_THREAD] = {f0, f1, f2, f3};
-        uint32_t code[PER_THREAD];
+    if (mode & M_INFECT) {
         bool any_cont_home = false;
 #pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const uint32_t fj = fs[j];
-            const bool ch = (fj & F_EPI_MASK) == EPI_C && at_own_household(fj) && !(fj & F_BIGHH);
-            any_cont_home |= ch;
-            code[j] = ((fj & F_HEAD) ? 0x8000u : 0u) | (ch ? 0x4000u : 0u) | ((fj & (F_BIGHH | F_FILLER)) ? 0x2000u : 0u) |
-                      ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 0x80u : 0u) | ((fj >> F_AGE_SHIFT) & F_AGE_MASK);
-        }
-        *reinterpret_cast<uint2*>(s_code + tid * PER_THREAD) = make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
-        *reinterpret_cast<uint4*>(s_thr + tid * PER_THREAD) = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < PER_THREAD; ++j)
+            any_cont_home |= (f[j] & (F_EPI_MASK | F_BIGHH)) == EPI_C && at_own_household(f[j]);
         tile_has_cont_home = __syncthreads_or(any_cont_home);
         if (tile_has_cont_home) {
-            // every household head sums its members' log-survival increments and publishes the threshold
+            // every household head sums the log-survival increments of its contagious members present
+            // (1 - prod(1 - 3 r_i), base_model.py:156-175, 184-187) and publishes the threshold to all members
 #pragma unroll 1
             for (int j = 0; j < PER_THREAD; ++j) {
-                const int o = tid * PER_THREAD + j;
-                uint32_t c = s_code[o];
-                if ((c & 0xA000u) != 0x8000u) continue;      // not a head, or big household / filler
+                const int o = o0 + j;
+                uint32_t c = s_f[o];
+                if ((c & (F_HEAD | F_BIGHH | F_FILLER)) != F_HEAD) continue;
                 int e = o;
                 unsigned long long hsum = 0ull;
                 const uint32_t* q = T.qfx;
-                bool have_q = false;
+                if (T.hw_rows > 1) q += (size_t)home_district(T, c, s_a[o], cid_tile + o, L0) * 256;
                 do {
-                    if (c & 0x4000u) {
-                        if (!have_q) {
-                            if (T.hw_rows > 1) q += (size_t)home_district(T, G.flags[slot0 + j], G.aux[slot0 + j], cid0 + j, L0) * 256;
-                            have_q = true;
-                        }
-                        hsum += __ldg(q + (c & 0xFFu));
-                    }
+                    if ((c & F_EPI_MASK) == EPI_C && at_own_household(c))
+                        hsum += __ldg(q + ((((c >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((c >> F_AGE_SHIFT) & F_AGE_MASK));
                     ++e;
                     if (e >= ABM_TILE) break;
-                    c = s_code[e];
-                } while (!(c & 0x8000u));
+                    c = s_f[e];
+                } while (!(c & F_HEAD));
                 if (hsum) {
                     const uint32_t thr = hazard_threshold(__dmul_rn((double)hsum, 1.0 / 4294967296.0));
                     for (int m = o; m < e; ++m) s_thr[m] = thr;
@@ -439,52 +412,168 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             __syncthreads();
         }
     } else {
-        __syncthreads();   // s_tally / s_cnt initialisation
+        __syncthreads();
     }
 
-    uint32_t cw0 = 0, cw1 = 0, cw2 = 0;    // packed per-status head counts of this thread (8 bits each)
-    uint32_t logc = 0;                     // packed "current" counters for the day log
-    bool changed_f = false, changed_a = false;
-
-#pragma unroll 1
-    for (int j = 0; j < PER_THREAD; ++j) {
-        uint32_t fj = f0, aj = a0;
-        const int64_t slot = slot0 + j, cid = cid0 + j;
-        // ------------------------------------------------------------ I(k-1): infection draw
-        if ((s.mode & M_INFECT) && (fj & F_EPI_MASK) == EPI_S) {
-            uint32_t thr = 0;
-            if (at_own_household(fj)) {
-                if (fj & F_BIGHH) {
-                    const unsigned long long hz = Wk.hbig_read[big_slot(T, cid)];
-                    if (hz) thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0));
-                } else if (tile_has_cont_home) {
-                    thr = s_thr[tid * PER_THREAD + j];
+    // ---------------------------------------------------------------- P1: classify own agents, build the queues
+    uint32_t logc = 0;     // packed "current" counters for the day log (state after I(k-1), before T(k))
+    {
+        int n_draw = 0;
+        uint32_t draw_mask = 0;
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const uint32_t fj = f[j], aj = a[j];
+            const int o = o0 + j;
+            if ((mode & M_INFECT) && (fj & F_EPI_MASK) == EPI_S) {
+                uint32_t thr = 0;
+                if (at_own_household(fj)) {
+                    if (fj & F_BIGHH) {
+                        const unsigned long long hz = Wk.hbig_read[big_slot(T, cid_tile + o)];
+                        if (hz) { thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0)); s_thr[o] = thr; }
+                    } else if (tile_has_cont_home) {
+                        thr = s_thr[o];
+                    }
+                } else {
+                    const int pool = pool_of(T, G, fj, aj, slot0 + j, cid_tile + o, L0);
+                    if (pool >= 0) {
+                        thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
+                        if (thr) s_thr[o] = thr;
+                    }
                 }
-            } else {
-                const int pool = pool_of(T, G, fj, aj, slot, cid, L0);
-                if (pool >= 0) thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
+                if (thr) { draw_mask |= 1u << j; ++n_draw; }
             }
-            if (thr) {
-                const U4 X = agent_draws(T, cid, s.k_inf, 0u);
-                if ((X.x >> 1) < thr) {
-                    fj = infect_agent(T, G, fj, aj, slot, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
-                    atomicAdd(s_tally + CUM_INFECTED, 1u);
+            if (mode & M_STEP) {
+                if (mode & M_LOG) {
+                    const uint32_t epi = fj & F_EPI_MASK, clin = (fj >> F_CLIN_SHIFT) & F_CLIN_MASK;
+                    logc += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
                 }
+                if ((aj & 0xFFFFu) <= (uint32_t)s.k) enqueue_one(s_n, s_q, Q_TRANS, o);
             }
         }
-        if (s.mode & M_STEP) {
-            // -------------------------------------------------------- log: "current" counters before T(k)
-            if (s.mode & M_LOG) {
-                const uint32_t epi = fj & F_EPI_MASK, clin = (fj >> F_CLIN_SHIFT) & F_CLIN_MASK;
-                logc += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+        if (mode & M_INFECT) {
+            // warp-aggregated append of the draw queue
+            int incl = n_draw;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
             }
-            // -------------------------------------------------------- T(k) transitions, M(k) movement
-            if ((aj & 0xFFFFu) <= (uint32_t)s.k) fj = transition_agent(T, G, fj, aj, slot, s.now, s_tally);
-            if ((s.mode & (M_GO_OUT | M_GO_HOME)) && !(fj & F_FILLER) && is_active(fj, aj)) {
-                if (s.mode & M_GO_HOME) fj = go_home_agent(T, G, fj, aj, slot, cid, s, L0);
-                if (s.mode & M_GO_OUT) fj = go_out_agent(T, G, fj, aj, slot, cid, s, L0);
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            int base = 0;
+            if (lane == 31 && total) base = (int)atomicAdd(s_n + Q_DRAW, (unsigned int)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - n_draw;
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; ++j)
+                if (draw_mask & (1u << j)) s_q[Q_DRAW * ABM_TILE + base++] = (uint16_t)(o0 + j);
+        }
+    }
+    __syncthreads();
+
+    if (mode & M_INFECT) {
+        // ------------------------------------------------------------ P2: the infection draws, all lanes busy
+        const int n_draw = (int)s_n[Q_DRAW];
+        for (int i = tid; i < n_draw; i += THREADS) {
+            const int o = s_q[Q_DRAW * ABM_TILE + i];
+            const U4 X = agent_draws(T, cid_tile + o, s.k_inf, 0u);
+            if ((X.x >> 1) < s_thr[o]) enqueue_one(s_n, s_q, Q_INFECT, o);
+        }
+        __syncthreads();
+        // ------------------------------------------------------------ P3: disease course of the newly infected
+        const int n_inf = (int)s_n[Q_INFECT];
+        for (int i = tid; i < n_inf; i += THREADS) {
+            const int o = s_q[Q_INFECT * ABM_TILE + i];
+            const int64_t slot = tile * ABM_TILE + o;
+            uint32_t aj = s_a[o];
+            const uint32_t fj = infect_agent(T, G, s_f[o], aj, slot, cid_tile + o, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+            s_f[o] = fj; s_a[o] = aj;
+            G.flags[slot] = fj; G.aux[slot] = aj;
+            atomicAdd(s_tally + CUM_INFECTED, 1u);
+            if (mode & M_STEP) {
+                if (mode & M_LOG) atomicAdd(s_tally + CUR_EXPOSED, 1u);
+                if ((aj & 0xFFFFu) <= (uint32_t)s.k) enqueue_one(s_n, s_q, Q_TRANS, o);
             }
-            // -------------------------------------------------------- A(k): pressure / headcount tables
+        }
+        if (mode & M_STEP) __syncthreads();
+    }
+
+    if (mode & M_STEP) {
+        // ------------------------------------------------------------ T(k): due transitions
+        const int n_trans = (int)s_n[Q_TRANS];
+        if (n_trans) {
+            for (int i = tid; i < n_trans; i += THREADS) {
+                const int o = s_q[Q_TRANS * ABM_TILE + i];
+                const int64_t slot = tile * ABM_TILE + o;
+                uint32_t aj = s_a[o];
+                const uint32_t fj = transition_agent(T, G, s_f[o], aj, slot, s.now, s_tally);
+                s_f[o] = fj; s_a[o] = aj;
+                G.flags[slot] = fj; G.aux[slot] = aj;
+            }
+        }
+        if (n_trans || (s_n[Q_INFECT] && (mode & M_INFECT))) {
+            __syncthreads();
+            const uint4 nf = *reinterpret_cast<const uint4*>(s_f + o0);
+            const uint4 na = *reinterpret_cast<const uint4*>(s_a + o0);
+            f[0] = nf.x; f[1] = nf.y; f[2] = nf.z; f[3] = nf.w;
+            a[0] = na.x; a[1] = na.y; a[2] = na.z; a[3] = na.w;
+        }
+        const uint32_t fb[PER_THREAD] = {f[0], f[1], f[2], f[3]};   // what global memory holds now
+        const uint32_t ab[PER_THREAD] = {a[0], a[1], a[2], a[3]};
+
+        // ------------------------------------------------------------ M(k): movement (base_model.py:274-441)
+        if (mode & (M_GO_OUT | M_GO_HOME)) {
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; ++j) {
+                uint32_t fj = f[j], aj = a[j];
+                if ((fj & F_FILLER) || !is_active(fj, aj)) continue;
+                const int o = o0 + j;
+                const int64_t slot = slot0 + j, cid = cid_tile + o;
+                if (mode & M_GO_HOME) {                                                    // :274-302
+                    if (!(fj & F_AWAY)) {
+                        fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
+                    } else if (G.t_return[slot] < s.now) {
+                        aj = (aj & 0xFFFFu) | (home_district(T, fj, aj, cid, L0) << 16);
+                        fj = (fj & ~(F_AWAY | (F_LOC_MASK << F_LOC_SHIFT))) | (LOC_HOME << F_LOC_SHIFT);
+                    }
+                }
+                if (mode & M_GO_OUT) {                                                     // :304-340
+                    const bool mild = T.mild_active && (fj & F_ONSET) && (fj & F_EPI_MASK) < EPI_R;   // :212-219, :316
+                    const uint32_t thr = __ldg(T.move_thr + 4 * (uint32_t)__ldg(G.move_class + slot) + ((mode & M_WEEKDAY) ? 0 : 2) + (mild ? 1 : 0));
+                    if (thr) {
+                        const bool needs_od = (fj & F_DMOVER) != 0;
+                        U4 X = U4{0, 0, 0, 0};
+                        if (thr < 0x80000000u || needs_od) X = agent_draws(T, cid, s.k, 0u);
+                        if ((X.y >> 1) < thr) {                                            // :317-318 a mover
+                            if ((fj & F_AWAY) && G.t_return[slot] < s.now) {               // :342-360
+                                aj = (aj & 0xFFFFu) | (home_district(T, fj, aj, cid, L0) << 16);
+                                fj &= ~F_AWAY;
+                            }
+                            bool left = false;
+                            if (needs_od && !(fj & F_AWAY)) {                              // :366-370
+                                const uint32_t home = aj >> 16;
+                                const uint32_t dest = od_destination(T, X.z >> 1, s.weekday, home);
+                                if (dest != home) {                                        // :410-439
+                                    fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | F_AWAY | (LOC_DIST << F_LOC_SHIFT);
+                                    aj = (aj & 0xFFFFu) | (dest << 16);
+                                    s_thr[o] = X.w;            // the stay draw, consumed by the Q_STAY pass
+                                    s_a[o] = (home << 16) | dest;
+                                    enqueue_one(s_n, s_q, Q_STAY, o);
+                                    left = true;
+                                }
+                            }
+                            if (!left) fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_ECON << F_LOC_SHIFT);   // :331-339, :346-352
+                        }
+                    }
+                }
+                f[j] = fj; a[j] = aj;
+            }
+        }
+
+        // ------------------------------------------------------------ A(k): pressure / headcount tables
+        uint32_t cw0 = 0, cw1 = 0, cw2 = 0;    // packed per-status head counts of this thread (8 bits each)
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const uint32_t fj = f[j], aj = a[j];
+            const int64_t slot = slot0 + j, cid = cid_tile + o0 + j;
             const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
             const int pool = pool_of(T, G, fj, aj, slot, cid, L0);
             const bool cont = (fj & F_EPI_MASK) == EPI_C;
@@ -504,19 +593,14 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                 atomicAdd(Wk.hbig_write + big_slot(T, cid), (unsigned long long)q);
             }
         }
-        changed_f |= fj != f0;
-        changed_a |= aj != a0;
-        // rotate the register file: slot j+1 becomes the current one, the processed one goes to the back
-        f0 = f1; f1 = f2; f2 = f3; f3 = fj;
-        a0 = a1; a1 = a2; a2 = a3; a3 = aj;
-    }
 
-    // ---------------------------------------------------------------- write back what changed
-    if (changed_f) *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
-    if (changed_a) *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
+        // ------------------------------------------------------------ write back what movement changed
+        if (f[0] != fb[0] || f[1] != fb[1] || f[2] != fb[2] || f[3] != fb[3])
+            *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f[0], f[1], f[2], f[3]);
+        if (a[0] != ab[0] || a[1] != ab[1] || a[2] != ab[2] || a[3] != ab[3])
+            *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a[0], a[1], a[2], a[3]);
 
-    if (s.mode & M_STEP) {
-        if (s.mode & M_LOG) {
+        if (mode & M_LOG) {
             logc = __reduce_add_sync(0xFFFFFFFFu, logc);   // <= 128 per 8-bit field
             if (lane < 4) {
                 const unsigned int v = (logc >> (8 * lane)) & 0xFFu;
@@ -534,6 +618,15 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         }
     }
     __syncthreads();
+    if (mode & M_GO_OUT) {
+        // ------------------------------------------------------------ length of stay of the departing travellers
+        const int n_stay = (int)s_n[Q_STAY];
+        for (int i = tid; i < n_stay; i += THREADS) {
+            const int o = s_q[Q_STAY * ABM_TILE + i];
+            const uint32_t hd = s_a[o];
+            G.t_return[tile * ABM_TILE + o] = stay_return_tick(T, s_thr[o], s.weekday, hd >> 16, hd & 0xFFFFu, s.now);
+        }
+    }
     if (tid < N_TALLY) {
         const unsigned int v = s_tally[tid];
         if (v) {
@@ -542,7 +635,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                            (unsigned long long)v);
         }
     }
-    if ((s.mode & M_STEP) && tid >= 32 && tid < 32 + T.A) {
+    if ((mode & M_STEP) && tid >= 32 && tid < 32 + T.A) {
         const int b = tid - 32;
         if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)L0 * T.A + b, (unsigned long long)s_cnt[b]);
         const unsigned long long r = ((unsigned long long)s_rhi[b] << 16) + s_rlo[b];
