@@ -42,10 +42,19 @@ F_EKIND_SHIFT, F_EKIND_MASK = 28, 0x3     # economic-activity location kind (EKI
 F_BIGHH = 1 << 30                         # member of a household larger than BIG_HOUSEHOLD
 F_FILLER = 1 << 31                        # padding slot, not a person
 
-LOC_HOME, LOC_ECON, LOC_DIST, LOC_HOSP, LOC_DEAD = 0, 1, 2, 3, 4
+# location kinds say WHERE the agent is (the reference's location id follows from it):
+#   HOME      own household                                   -> household id
+#   CUR       outside pool of its current district            -> current_district id (economic activity in the
+#             home district, or the destination district of a trip; base_model.py:337-339, 436-439)
+#   HOMEPOOL  outside pool of the HOME district while away    -> home district id (quirk Q4)
+#   POOL      extra outside location (school)                 -> its economic_activity_location id
+#   HOSP      hospital = -current_district (base_model.py:270-272);  DEAD = -1
+LOC_HOME, LOC_CUR, LOC_HOMEPOOL, LOC_POOL, LOC_HOSP, LOC_DEAD = 0, 1, 2, 3, 4, 5
 EKIND_HOUSEHOLD, EKIND_HOME_DISTRICT, EKIND_POOL = 0, 1, 2
 
-TILE = 1024           # agent slots per tile; no household of <= BIG_HOUSEHOLD members straddles a tile
+TILE = 1024           # agent slots per thread block (8 warps x SUBTILE)
+SUBTILE = 128         # slots per warp: whole households (<= BIG_HOUSEHOLD members) of ONE home district; slot
+                      # offset o of a sub-tile holds canonical agent id base + o with base a multiple of 4
 BIG_HOUSEHOLD = 32    # larger households (mining camps, scenario_models.py:232-236) use the atomic path
 MAX_STATUS = 12       # packed headcount reduction holds 12 statuses (3 words x 4 x 8 bit)
 

@@ -40,7 +40,7 @@ class AbmConfig(ct.Structure):
 class AbmTables(ct.Structure):
     _fields_ = [(n, ct.c_void_p) for n in
                 ('rfx', 'qfx', 'W', 'pool_hw', 'od_thr', 'stay_par', 'dwell', 'znorm', 'p_hosp', 'p_crit', 'p_hfat',
-                 'severe_risk', 'move_thr', 'district_start', 'tile_base', 'tile_home', 'big_start')]
+                 'severe_risk', 'move_thr', 'sub_info', 'big_start')]
 
 
 class AbmAgentPtrs(ct.Structure):
@@ -118,7 +118,7 @@ class Simulation:
         self.spec, self.pop = spec, pop
         self.tab = tables if tables is not None else tables_mod.build_tables(spec)
         self.device = torch.device('cuda', device)
-        self.sm = layout.build_slot_map(pop.household, agent_id_base)
+        self.sm = layout.build_slot_map(pop.household, pop.district, agent_id_base)
         sm = self.sm
         D = spec.n_districts
         if district_start is None:
@@ -147,7 +147,6 @@ class Simulation:
         )
         if pop.econ_pool is not None:
             self.buf['econ_pool'] = dev(slots_from_agents(pop.econ_pool.astype(np.int32), 0, np.int32))
-        tile_home = pop.district[np.clip(sm.tile_base[:-1] - agent_id_base, 0, pop.n - 1)].astype(np.uint16)
 
         cfg = AbmConfig()
         cfg.n_slots, cfg.n_tiles, cfg.agent_id_base = n_slots, sm.n_tiles, agent_id_base
@@ -177,8 +176,7 @@ class Simulation:
         keep = dict(
             rfx=t['rfx'], qfx=t['qfx'], W=t['W'], pool_hw=t['pool_hw'], od_thr=t['od_thr'], stay_par=t['stay_par'],
             dwell=t['dwell'], znorm=t['znorm'], p_hosp=t['p_hosp'], p_crit=t['p_crit'], p_hfat=t['p_hfat'],
-            severe_risk=t['severe_risk'], move_thr=self.move_thr, district_start=self.district_start,
-            tile_base=np.ascontiguousarray(sm.tile_base), tile_home=np.ascontiguousarray(tile_home),
+            severe_risk=t['severe_risk'], move_thr=self.move_thr, sub_info=np.ascontiguousarray(sm.sub_info),
             big_start=np.ascontiguousarray(sm.big_start))
         at = AbmTables()
         for name, arr in keep.items():

@@ -1,6 +1,7 @@
 """Structure-of-arrays agent store: host-side packing / unpacking.
 
-Device layout (one slot per agent, slots grouped in tiles of TILE = 1024):
+Device layout (one slot per agent; sub-tiles of SUBTILE = 128 slots, one per warp; tiles of TILE = 1024
+slots, one per thread block):
   hot, read every sub-step (8 B/agent):
     flags  uint32   bit fields of constants.F_*  (epidemic / clinical / symptomatic state, location kind,
                     away, district_mover, economic status, age, household-head bit, outcome bits, ...)
@@ -9,12 +10,15 @@ Device layout (one slot per agent, slots grouped in tiles of TILE = 1024):
   cold, touched only when an event fires, on infection, or on the two movement sub-steps for travellers:
     t_infected, t_contagious, t_onset, t_recovered, t_return   int32 minute ticks
     inf_at uint32   (location kind << 16) | district at infection
-    move_class uint16  index into the movement-probability threshold table
+    move_class uint16  index into the movement-probability threshold table (read at go_out only)
     econ_pool  uint32  outside-pool row for EKIND_POOL agents (schools), allocated only when used
-Agents are in canonical order (home district, household).  Filler slots are appended at the end of a
-tile whenever the next household (of <= BIG_HOUSEHOLD members) would straddle a tile boundary, so a
-thread block always sees whole households; households larger than that are flagged F_BIGHH and use a
-global-atomic path.  `tile_base[t]` is the canonical id of the first agent of tile t.
+Agents are in canonical order (home district, household).  A sub-tile holds whole households (of
+<= BIG_HOUSEHOLD members) of ONE home district, and slot offset o of a sub-tile holds canonical agent id
+base + o with base a multiple of 4: when the id b of its first agent is not, the first b & 3 slots are
+fillers.  So a warp sees whole households, the home district is a per-warp scalar, and the four agents
+of a lane share one Philox group (id >> 2).  Remaining slots at the end of a sub-tile are fillers too.
+Households larger than BIG_HOUSEHOLD are flagged F_BIGHH, placed member by member and use a
+global-atomic path.  `sub_info[u]` = base | home_district << 48.
 
 This mirrors what Country.initialize_agent_vectors / initialize_epidemic_vectors build
 (/root/reference/src/covid19_abm/base_model.py:527-634) with 31 eight-byte vectors per agent.
@@ -27,26 +31,45 @@ from . import constants as C
 from .spec import Population
 
 T_NEVER = int(C.T_NEVER)
+SUBS_PER_TILE = C.TILE // C.SUBTILE
 
 
 @dataclass
 class SlotMap:
     n_agents: int
-    n_tiles: int
-    tile_base: np.ndarray      # int64 [n_tiles + 1] canonical (global) id of first agent per tile
+    n_tiles: int               # thread-block tiles of TILE slots
+    n_subtiles: int            # n_tiles * SUBS_PER_TILE (trailing ones may be empty)
+    sub_first: np.ndarray      # int64 [n_subtiles + 1] local index of the first agent of each sub-tile
+    sub_lead: np.ndarray       # int64 [n_subtiles] filler slots at the start of each sub-tile (0..3)
+    sub_home: np.ndarray       # int64 [n_subtiles] home district of the agents of each sub-tile
     slot_of: np.ndarray        # int64 [n_agents] local agent -> slot
-    agent_of: np.ndarray       # int64 [n_slots] slot -> local agent, -1 for fillers
     big_start: np.ndarray      # int64 [n_big + 1] global id of first member of each big household (+ sentinel)
     big_size: np.ndarray       # int64 [n_big]
     agent_id_base: int
+    _agent_of: np.ndarray = None
 
     @property
     def n_slots(self):
         return self.n_tiles * C.TILE
 
+    @property
+    def agent_of(self):
+        """int64 [n_slots] slot -> local agent, -1 for fillers."""
+        if self._agent_of is None:
+            a = np.full(self.n_slots, -1, dtype=np.int64)
+            a[self.slot_of] = np.arange(self.n_agents, dtype=np.int64)
+            self._agent_of = a
+        return self._agent_of
 
-def build_slot_map(household: np.ndarray, agent_id_base: int = 0) -> SlotMap:
-    """Greedy tile packing.  Units are whole small households and single members of big ones."""
+    @property
+    def sub_info(self):
+        """uint64 [n_subtiles]: canonical id of slot 0 (a multiple of 4) | home district << 48."""
+        base = self.sub_first[:-1] + self.agent_id_base - self.sub_lead
+        return (base.astype(np.uint64) | (self.sub_home.astype(np.uint64) << np.uint64(48)))
+
+
+def build_slot_map(household: np.ndarray, district: np.ndarray, agent_id_base: int = 0) -> SlotMap:
+    """Greedy sub-tile packing.  Units are whole small households and single members of big ones."""
     n = int(household.shape[0])
     if n == 0:
         raise ValueError('empty population')
@@ -61,26 +84,46 @@ def build_slot_map(household: np.ndarray, agent_id_base: int = 0) -> SlotMap:
     unit_rep = np.where(big, sizes, 1)
     unit_len = np.repeat(unit_size, unit_rep)                 # length of each unit
     unit_end = np.cumsum(unit_len)                            # agents consumed after each unit
-    tile_first = [0]                                          # first agent of each tile
-    pos = 0
-    while pos < n:
-        # last unit whose end <= pos + TILE
-        j = int(np.searchsorted(unit_end, pos + C.TILE, side='right'))
-        nxt = int(unit_end[j - 1]) if j > 0 else pos
-        if nxt <= pos:
-            raise RuntimeError('placement unit larger than a tile')
-        pos = nxt
-        tile_first.append(pos)
-    tile_first = np.array(tile_first, dtype=np.int64)
-    n_tiles = tile_first.shape[0] - 1
-    tile_of_agent = np.searchsorted(tile_first, np.arange(n, dtype=np.int64), side='right') - 1
-    slot_of = tile_of_agent * C.TILE + (np.arange(n, dtype=np.int64) - tile_first[tile_of_agent])
-    agent_of = np.full(n_tiles * C.TILE, -1, dtype=np.int64)
-    agent_of[slot_of] = np.arange(n, dtype=np.int64)
+    unit_start = unit_end - unit_len
+    m = unit_start.shape[0]
+    # a sub-tile never continues into another home district
+    d_unit = np.asarray(district)[unit_start]
+    brk = np.nonzero(np.r_[True, d_unit[1:] != d_unit[:-1]])[0]         # units that start a district
+    next_brk = np.r_[brk[1:], m][np.searchsorted(brk, np.arange(m), side='right') - 1]
+    # capacity of a sub-tile that starts with unit i: the leading (id & 3) slots are fillers
+    lead_unit = (unit_start + agent_id_base) & 3
+    nxt = np.minimum(np.searchsorted(unit_end, unit_start + (C.SUBTILE - lead_unit), side='right'), next_brk)
+    if np.any(nxt <= np.arange(m)):
+        raise RuntimeError('placement unit larger than a sub-tile')
+    nxt_l = nxt.tolist()
+    chain = [0]
+    i = 0
+    while i < m:                      # one hop per sub-tile
+        i = nxt_l[i]
+        chain.append(i)
+    chain = np.array(chain, dtype=np.int64)
+    first_unit = chain[:-1]
+    n_sub_used = first_unit.shape[0]
+    sub_first = np.r_[unit_start[first_unit], n].astype(np.int64)
+    sub_lead = lead_unit[first_unit].astype(np.int64)
+    sub_home = d_unit[first_unit].astype(np.int64)
+    n_tiles = (n_sub_used + SUBS_PER_TILE - 1) // SUBS_PER_TILE
+    pad = n_tiles * SUBS_PER_TILE - n_sub_used
+    counts = np.diff(sub_first)
+    if np.any(counts + sub_lead > C.SUBTILE):
+        raise RuntimeError('sub-tile overflow')
+    shift = np.arange(n_sub_used, dtype=np.int64) * C.SUBTILE + sub_lead - sub_first[:-1]
+    slot_of = np.arange(n, dtype=np.int64) + np.repeat(shift, counts)
+    # empty trailing sub-tiles: all fillers, ids past the last agent (rounded up to a multiple of 4)
+    end_id = n + agent_id_base
+    pad_lead = np.full(pad, end_id & 3, dtype=np.int64)       # keeps base = end_id - lead a multiple of 4
+    sub_first = np.r_[sub_first, np.full(pad, n, dtype=np.int64)]
+    sub_lead = np.r_[sub_lead, pad_lead]
+    sub_home = np.r_[sub_home, np.zeros(pad, dtype=np.int64)]
     big_start = np.append(starts[big], n).astype(np.int64) + agent_id_base
-    return SlotMap(n_agents=n, n_tiles=n_tiles, tile_base=tile_first + agent_id_base, slot_of=slot_of,
-                   agent_of=agent_of, big_start=big_start, big_size=sizes[big].astype(np.int64),
-                   agent_id_base=int(agent_id_base))
+    return SlotMap(n_agents=n, n_tiles=n_tiles, n_subtiles=n_tiles * SUBS_PER_TILE, sub_first=sub_first,
+                   sub_lead=sub_lead, sub_home=sub_home, slot_of=slot_of, big_start=big_start,
+                   big_size=sizes[big].astype(np.int64), agent_id_base=int(agent_id_base))
 
 
 def pack_flags(pop: Population, sm: SlotMap):
@@ -139,8 +182,9 @@ def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_ho
         econ_loc = np.where(pop.econ_kind == C.EKIND_POOL, D + H + (pop.econ_pool.astype(np.int64) - D), econ_loc)
 
     def loc_from(kind, cur):
-        return np.select([kind == C.LOC_HOME, kind == C.LOC_ECON, kind == C.LOC_DIST, kind == C.LOC_HOSP],
-                         [household_ids, econ_loc, cur, -cur], default=-1)
+        return np.select([kind == C.LOC_HOME, kind == C.LOC_CUR, kind == C.LOC_HOMEPOOL, kind == C.LOC_POOL,
+                          kind == C.LOC_HOSP],
+                         [household_ids, cur, pop.district.astype(np.int64), econ_loc, -cur], default=-1)
 
     away = (f & C.F_AWAY) != 0
     infected = dev['t_infected'][s] != T_NEVER

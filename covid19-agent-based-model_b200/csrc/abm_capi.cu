@@ -37,11 +37,12 @@ struct abm_handle {
     DevAgents G{};
     bool have_tables = false, have_agents = false;
     std::vector<void*> owned;           // device allocations to free
-    unsigned long long* acc = nullptr;  // [2][P][A]
-    unsigned long long* acc_snapshot = nullptr;
+    unsigned long long* acc[2] = {nullptr, nullptr};   // [2][P][A] each; sub-step k accumulates into acc[k & 1]
     uint32_t* thr_out = nullptr;        // [P][A]
     unsigned long long* hbig[2] = {nullptr, nullptr};
-    unsigned long long* cum = nullptr;  // [N_TALLY]
+    unsigned long long* tally = nullptr;   // [N_TALLY] per-launch event tallies, folded by the table kernel
+    long long* counters = nullptr;      // [12] running cumulative (0..7) and current (8..11) counters
+    bool daytime = false;               // between go_out and go_home: most agents are in an outside pool
     long long* daylog = nullptr;        // [max_log_rows + 1][ABM_LOG_STRIDE]; last row is scratch
     uint32_t* move_thr = nullptr;
     int32_t n_move_classes = 0;
@@ -109,14 +110,13 @@ int32_t weekday_of(const abm_config& c, int64_t tick) {
     return (int32_t)((c.start_weekday + (c.start_minute_of_day + tick) / 1440) % 7);
 }
 
-int launch_main(abm_handle* h, const StepArgs& s, long long* log_row) {
+int launch_main(abm_handle* h, const StepArgs& s) {
     DevWork w{};
-    w.acc = h->acc;
+    w.acc = h->acc[s.k & 1];
     w.thr_out = h->thr_out;
     w.hbig_write = h->hbig[s.k & 1];
     w.hbig_read = h->hbig[(s.k + 1) & 1];
-    w.cum = h->cum;
-    w.log_row = log_row;
+    w.tally = h->tally;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->prof_used == h->prof_events.size()) {
@@ -130,13 +130,16 @@ int launch_main(abm_handle* h, const StepArgs& s, long long* log_row) {
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
     const dim3 grid((unsigned)h->cfg.n_tiles), block(THREADS);
-    const uint32_t m = s.mode & ~M_WEEKDAY;
-    // the four sub-step kinds of a simulated day get their own instantiation; anything else is generic
-    if (m == (M_INFECT | M_STEP)) abm_substep_kernel<M_INFECT | M_STEP><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
-    else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_LOG)) abm_substep_kernel<M_INFECT | M_STEP | M_GO_OUT | M_LOG><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
-    else if (m == (M_INFECT | M_STEP | M_GO_HOME)) abm_substep_kernel<M_INFECT | M_STEP | M_GO_HOME><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
-    else if (m == M_INFECT) abm_substep_kernel<M_INFECT><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
-    else abm_substep_kernel<RUNTIME_MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s);
+    const uint32_t m = s.mode & ~(M_WEEKDAY | M_LOG);
+    // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
+#define ABM_LAUNCH(MODE) abm_substep_kernel<MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s)
+    if (m == (M_INFECT | M_STEP)) ABM_LAUNCH(M_INFECT | M_STEP);                                        // night
+    else if (m == (M_INFECT | M_STEP | M_DENSE)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE);               // day
+    else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE);
+    else if (m == (M_INFECT | M_STEP | M_GO_HOME)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_HOME);
+    else if (m == M_INFECT) ABM_LAUNCH(M_INFECT);                                                       // abm_flush
+    else ABM_LAUNCH(RUNTIME_MODE);
+#undef ABM_LAUNCH
     if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -197,12 +200,13 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     h->stream = (cudaStream_t)cfg->stream;   // NULL is the legacy default stream, which is also torch's default
     const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
     int rc;
-    if ((rc = alloc_zero(h, 2 * pa, &h->acc))) return rc;
-    if ((rc = alloc_zero(h, 2 * pa, &h->acc_snapshot))) return rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc[0]))) return rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc[1]))) return rc;
     if ((rc = alloc_zero(h, pa, &h->thr_out))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[0]))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[1]))) return rc;
-    if ((rc = alloc_zero(h, (size_t)N_TALLY, &h->cum))) return rc;
+    if ((rc = alloc_zero(h, (size_t)N_TALLY, &h->tally))) return rc;
+    if ((rc = alloc_zero(h, (size_t)12, &h->counters))) return rc;
     if ((rc = alloc_zero(h, (size_t)(cfg->max_log_rows + 1) * ABM_LOG_STRIDE, &h->daylog))) return rc;
     if (cfg->world_size > 1) {
         if (!cfg->nccl_unique_id) return fail(h, ABM_ERR_ARG, "world_size > 1 needs an ncclUniqueId");
@@ -244,14 +248,19 @@ int abm_set_tables(abm_handle* h, const abm_tables* t) {
     if ((rc = upload(h, t->move_thr, (size_t)c.n_move_classes * 4, &mt))) return rc;
     T.move_thr = mt;
     h->n_move_classes = c.n_move_classes;
-    if ((rc = upload(h, t->district_start, D + 1, &T.district_start))) return rc;
-    if ((rc = upload(h, t->tile_base, (size_t)c.n_tiles + 1, &T.tile_base))) return rc;
-    if ((rc = upload(h, t->tile_home, (size_t)c.n_tiles, &T.tile_home))) return rc;
+    {
+        const unsigned long long* si = nullptr;
+        if ((rc = upload(h, reinterpret_cast<const unsigned long long*>(t->sub_info), (size_t)c.n_tiles * (ABM_TILE / ABM_SUBTILE), &si))) return rc;
+        T.sub_info = si;
+    }
     if ((rc = upload(h, t->big_start, (size_t)c.n_big_households + 1, &T.big_start))) return rc;
     T.D = c.n_districts; T.A = c.n_status; T.P = c.n_pools; T.hw_rows = c.hw_rows; T.n_big = c.n_big_households;
     T.step_ticks = c.step_ticks; T.mild_active = c.mild_active;
     T.step_inv = ~0ull / (unsigned long long)c.step_ticks + 1ull;   // floor(2^64 / step) + 1 for step >= 2 not a power of two; exact use in fire_index
-    T.seed_lo = (uint32_t)c.seed; T.seed_hi = (uint32_t)(c.seed >> 32);
+    for (int r = 0; r < 10; ++r) {      // Philox4x32 key schedule
+        T.rk[2 * r] = (uint32_t)c.seed + (uint32_t)r * 0x9E3779B9u;
+        T.rk[2 * r + 1] = (uint32_t)(c.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     T.symptomatic_rate = c.symptomatic_rate; T.critical_fatality_rate = c.critical_fatality_rate;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // host staging buffers may be released by the caller
     h->have_tables = true;
@@ -298,7 +307,7 @@ int abm_seed(abm_handle* h, const int64_t* slots, const int64_t* ids, int64_t n)
     CUDA_TRY(h, cudaMemcpyAsync(d_slots, slots, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(d_ids, ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     const int32_t now = (int32_t)(h->k * h->cfg.step_ticks);
-    abm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->T, h->G, h->cum, d_slots, d_ids, n, (int32_t)h->k, now);
+    abm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->T, h->G, h->tally, d_slots, d_ids, n, (int32_t)h->k, now);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d_slots);
@@ -321,8 +330,9 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
         StepArgs s{};
         s.k = (int32_t)h->k; s.now = (int32_t)tick; s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks; s.weekday = wd;
         s.mode = M_STEP | (h->pending_infect ? M_INFECT : 0u);
-        if (hour == 8) s.mode |= M_GO_OUT;            // params.py:131,135
-        if (hour == 16) s.mode |= M_GO_HOME;          // params.py:132,136
+        if (hour == 8) { s.mode |= M_GO_OUT; h->daytime = true; }     // params.py:131,135
+        if (hour == 16) { s.mode |= M_GO_HOME; h->daytime = false; }  // params.py:132,136
+        if (h->daytime) s.mode |= M_DENSE;
         if (wd <= 4) s.mode |= M_WEEKDAY;             // base_model.py:309
         const bool log = hour == 8;                   // base_model.py:1083
         long long* row = h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE;   // scratch row
@@ -331,10 +341,11 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
             s.mode |= M_LOG;
             row = h->daylog + (size_t)h->n_log_rows * ABM_LOG_STRIDE;
         }
-        int rc = launch_main(h, s, row);
+        int rc = launch_main(h, s);
         if (rc) return rc;
+        unsigned long long* acc = h->acc[s.k & 1];
         if (h->comm) {
-            ncclResult_t r = h->nccl_allreduce(h->acc, h->acc, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
+            ncclResult_t r = h->nccl_allreduce(acc, acc, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
             if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
         }
         TableArgs ta{};
@@ -343,12 +354,11 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
         ta.seeds_before_now = 0;
         for (const SeedEvent& e : h->seeds)
             if (e.tick < tick) ta.seeds_before_now += e.n;
-        const int nthreads = pa > c.n_big_households ? pa : c.n_big_households;
-        abm_hazard_table_kernel<<<(nthreads + 127) / 128, 128, 0, h->stream>>>(h->T, h->acc, h->acc_snapshot, h->thr_out,
-                                                                              h->hbig[(s.k + 1) & 1], h->cum, row, ta);
-        abm_clear_tables_kernel<<<(2 * pa + 127) / 128, 128, 0, h->stream>>>(h->acc, h->acc_snapshot, 2 * pa);
+        const int nthreads = 2 * pa > c.n_big_households ? 2 * pa : c.n_big_households;
+        abm_hazard_table_kernel<<<(nthreads + 127) / 128, 128, 0, h->stream>>>(h->T, acc, h->acc[(s.k + 1) & 1], h->thr_out,
+                                                                              h->hbig[(s.k + 1) & 1], h->tally, h->counters, row, ta);
         CUDA_TRY(h, cudaGetLastError());
-        h->launches += 2;
+        h->launches += 1;
         if (log) h->n_log_rows++;
         h->k++;
         h->pending_infect = true;
@@ -364,7 +374,7 @@ int abm_flush(abm_handle* h) {
     s.k = (int32_t)h->k; s.now = (int32_t)(h->k * c.step_ticks); s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks;
     s.weekday = weekday_of(c, s.now);
     s.mode = M_INFECT;
-    int rc = launch_main(h, s, h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE);
+    int rc = launch_main(h, s);
     if (rc) return rc;
     h->pending_infect = false;
     return ABM_OK;
@@ -394,11 +404,14 @@ int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
     CUDA_TRY(h, cudaMemsetAsync(d4, 0, 4 * sizeof(unsigned long long), h->stream));
     const int64_t n = h->cfg.n_slots;
     abm_count_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->G, n, d4);
-    unsigned long long cur[4], cum[N_TALLY];
+    unsigned long long cur[4], pend[N_TALLY];
+    long long run[12], cum[8];
     CUDA_TRY(h, cudaMemcpyAsync(cur, d4, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(cum, h->cum, sizeof cum, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(pend, h->tally, sizeof pend, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(run, h->counters, sizeof run, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d4);
+    for (int i = 0; i < 8; ++i) cum[i] = run[i] + (long long)pend[i];   // tallies of a flush are folded by the next table kernel
     h->launches++;
     // NOTE: cumulative date counters cover events whose date precedes the LAST executed sub-step's clock;
     // the day log (abm_read_log) holds the exact log_model_output values.
@@ -442,8 +455,10 @@ int abm_district_symptomatic(abm_handle* h, int64_t* sym, int64_t* pop) {
 int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* thr) {
     if (!h) return ABM_ERR_ARG;
     const size_t pa = (size_t)h->cfg.n_pools * h->cfg.n_status;
-    if (rsum) CUDA_TRY(h, cudaMemcpyAsync(rsum, h->acc_snapshot, pa * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (ncnt) CUDA_TRY(h, cudaMemcpyAsync(ncnt, h->acc_snapshot + pa, pa * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->k < 1) return fail(h, ABM_ERR_STATE, "no sub-step executed yet");
+    const unsigned long long* last = h->acc[(h->k - 1) & 1];    // tables of the last executed sub-step
+    if (rsum) CUDA_TRY(h, cudaMemcpyAsync(rsum, last, pa * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (ncnt) CUDA_TRY(h, cudaMemcpyAsync(ncnt, last + pa, pa * 8, cudaMemcpyDeviceToHost, h->stream));
     if (thr) CUDA_TRY(h, cudaMemcpyAsync(thr, h->thr_out, pa * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ABM_OK;

@@ -5,18 +5,29 @@
 //           household hazard (reference: EpidemicScheduler.step location loop, base_model.py:60-175, in
 //           its pressure-table form) and, on infection, the whole disease course
 //           (Country.set_epidemic_status, base_model.py:838-1055)
-//   log     the four "current" counters of Country.log_model_output (base_model.py:1092-1095) at hour 8
 //   T(k)    time-to-next-event transitions (update_agent_states, base_model.py:226-272) and the
 //           contagious promotion (base_model.py:54-58)
 //   M(k)    go_home at hour 16 / go_out + OD mobility at hour 8 (base_model.py:274-441)
 //   A(k)    accumulation of the district x status infectious-pressure and headcount tables
 // Fusing I(k-1) into the launch of sub-step k means the 8-byte hot record of an agent is read once
 // per sub-step.  abm_hazard_table_kernel then turns the accumulated tables into 31-bit Bernoulli
-// thresholds for the next launch.
+// thresholds for the next launch and keeps the day log (Country.log_model_output, base_model.py:1082-1106).
 //
-// All random numbers are Philox4x32-10 keyed (seed; agent id, sub-step, site).  Everything that is
-// compared against the oracle is integer arithmetic or IEEE double +,*,/ through the __d*_rn
-// intrinsics (never contracted to FMA), so results are bit-identical to oracle/abm_oracle.py.
+// Execution model: ONE WARP OWNS ONE SUB-TILE of 128 consecutive agent slots (lane l holds slots
+// 4l..4l+3, one 128-bit load per hot word).  The host layout guarantees that a sub-tile holds whole
+// households of a single home district and that slot offset o of a sub-tile is canonical agent id
+// base + o with base a multiple of 4, so (a) the household hazard is a warp-local segmented sum,
+// (b) the home district is a per-warp scalar and (c) one Philox4x32 block serves the four agents of a
+// lane.  Warps never wait for each other except for one block-wide flush of the per-CTA counters.
+// Work that only a few agents need (disease-course sampling, due transitions, travellers) runs in
+// "funnel" loops: every lane keeps a bit mask of its agents that need it and the warp iterates until
+// all masks are empty, so the cost is max-per-lane, not four passes.
+//
+// All random numbers are Philox4x32-10 keyed by the seed.  Counter = (id, id >> 32, sub-step, site):
+// id = agent_id >> 2 for the group sites (word agent_id & 3 belongs to the agent), id = agent_id for
+// the disease-course sites.  Everything that is compared against the oracle is integer arithmetic or
+// IEEE double +,*,/ through the __d*_rn intrinsics (never contracted to FMA), so results are
+// bit-identical to oracle/abm_oracle.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,34 +43,44 @@ constexpr uint32_t F_AWAY = 1u << 10, F_DMOVER = 1u << 11;
 constexpr uint32_t F_STATUS_SHIFT = 12, F_STATUS_MASK = 0xFu, F_AGE_SHIFT = 16, F_AGE_MASK = 0x7Fu;
 constexpr uint32_t F_HEAD = 1u << 23, F_OUT_H = 1u << 24, F_OUT_C = 1u << 25, F_OUT_D = 1u << 26, F_ONSET = 1u << 27;
 constexpr uint32_t F_EKIND_SHIFT = 28, F_EKIND_MASK = 0x3u, F_BIGHH = 1u << 30, F_FILLER = 1u << 31;
-constexpr uint32_t LOC_HOME = 0, LOC_ECON = 1, LOC_DIST = 2, LOC_HOSP = 3, LOC_DEAD = 4;
+// where the agent is: own household / outside pool of its current district / outside pool of its HOME
+// district while away (quirk Q4) / extra outside pool (school) / hospital (-current_district) / dead
+constexpr uint32_t LOC_HOME = 0, LOC_CUR = 1, LOC_HOMEPOOL = 2, LOC_POOL = 3, LOC_HOSP = 4, LOC_DEAD = 5;
 constexpr uint32_t EKIND_HOUSEHOLD = 0, EKIND_HOME_DISTRICT = 1, EKIND_POOL = 2;
 constexpr uint32_t EPI_S = 0, EPI_I = 1, EPI_C = 2, EPI_R = 3, EPI_D = 4;
 constexpr int32_t T_NEVER = 0x7FFFFFFF;
 constexpr uint32_t FIRE_NEVER = 0xFFFFu;
 constexpr int32_t DAY = 1440;
+constexpr uint32_t LOCF = F_LOC_MASK << F_LOC_SHIFT;
+
+// ---- Philox sites (oracle/philox.py)
+constexpr uint32_t SITE_INFECT = 0, SITE_COURSE_A = 1, SITE_COURSE_B = 2, SITE_MOVER = 3, SITE_OD = 4, SITE_STAY = 5;
 
 // ---- step modes
-constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32;
+constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32, M_DENSE = 64;
 
-// ---- cumulative counters (device array cum[])
+// ---- counters.  cum[]: events whose date has passed (cumulative log columns); cur deltas are split in
+// "pre" (infection phase: part of the state the day log sees) and "post" (transition phase: after it)
 enum { CUM_CONTAGIOUS = 0, CUM_INFECTED, CUM_HOSPITALIZED, CUM_CRITICAL, CUM_DIED, CUM_RECOVERED, CUM_ASYM, CUM_SYM,
-       CUR_EXPOSED, CUR_CONTAGIOUS, CUR_HOSPITALIZED, CUR_CRITICAL, N_TALLY };
+       PRE_EXPOSED, PRE_CONTAGIOUS, PRE_HOSPITALIZED, PRE_CRITICAL,
+       POST_EXPOSED, POST_CONTAGIOUS, POST_HOSPITALIZED, POST_CRITICAL, N_TALLY };
 
 constexpr int THREADS = 256;
-constexpr int PER_THREAD = 4;
-static_assert(THREADS * PER_THREAD == ABM_TILE, "one tile per block");
+constexpr int WARPS = THREADS / 32;
+constexpr int PER_LANE = 4;
+constexpr int SUB = ABM_SUBTILE;
+static_assert(WARPS * SUB == ABM_TILE && PER_LANE * 32 == SUB, "one sub-tile per warp, one tile per block");
+constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 struct DevTables {
     const uint32_t* rfx; const uint32_t* qfx; const double* W; const double* pool_hw;
     const uint32_t* od_thr; const double* stay_par; const uint32_t* dwell; const int32_t* znorm;
     const double* p_hosp; const double* p_crit; const double* p_hfat; const double* severe_risk;
-    const uint32_t* move_thr; const int64_t* district_start; const int64_t* tile_base;
-    const uint16_t* tile_home; const int64_t* big_start;
+    const uint32_t* move_thr; const unsigned long long* sub_info; const int64_t* big_start;
     int32_t D, A, P, hw_rows, n_big, step_ticks, mild_active;
-    uint32_t seed_lo, seed_hi;
     unsigned long long step_inv;    // floor(2^64 / step_ticks) + 1
     double symptomatic_rate, critical_fatality_rate;
+    uint32_t rk[20];                // Philox round keys (k0, k1) x 10
 };
 
 struct DevAgents {
@@ -69,12 +90,11 @@ struct DevAgents {
 };
 
 struct DevWork {
-    unsigned long long* acc;        // [2][P][A]: R fixed-point sums, then head counts
+    unsigned long long* acc;        // [2][P][A] of THIS sub-step: R fixed-point sums, then head counts
     const uint32_t* thr_out;        // [P][A] thresholds from the previous sub-step
     unsigned long long* hbig_read;  // [n_big] household hazard of big households, previous sub-step
     unsigned long long* hbig_write; // [n_big] accumulated this sub-step
-    unsigned long long* cum;        // [N_TALLY]
-    long long* log_row;             // day-log row written when M_LOG
+    unsigned long long* tally;      // [N_TALLY]
 };
 
 struct StepArgs {
@@ -89,22 +109,27 @@ struct StepArgs {
 // ------------------------------------------------------------------------------------------------ Philox
 struct U4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ U4 philox4x32_10(const DevTables& T, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ T.rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ T.rk[2 * r + 1];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return U4{c0, c1, c2, c3};
 }
-
+// one block per agent (disease-course sites)
 __device__ __forceinline__ U4 agent_draws(const DevTables& T, int64_t cid, int32_t step, uint32_t site) {
-    return philox4x32_10((uint32_t)cid, (uint32_t)((uint64_t)cid >> 32), (uint32_t)step, site, T.seed_lo, T.seed_hi);
+    return philox4x32_10(T, (uint32_t)cid, (uint32_t)((uint64_t)cid >> 32), (uint32_t)step, site);
 }
+// one block per group of four consecutive agent ids; word (cid & 3) belongs to agent cid
+__device__ __forceinline__ U4 group_draws(const DevTables& T, int64_t cid4, int32_t step, uint32_t site) {
+    const uint64_t g = (uint64_t)cid4 >> 2;
+    return philox4x32_10(T, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, site);
+}
+__device__ __forceinline__ uint32_t word_of(const U4& X, int j) { return j == 0 ? X.x : (j == 1 ? X.y : (j == 2 ? X.z : X.w)); }
 
 // Bernoulli with probability p on a 32-bit draw: (x >> 1) / 2^31 < p, as an exact double comparison.
 __device__ __forceinline__ bool bernoulli(uint32_t x, double p) {
@@ -155,21 +180,6 @@ __device__ __forceinline__ uint32_t fire_index(int32_t t, unsigned long long ste
     return f < 0xFFFEu ? f : 0xFFFEu;
 }
 
-// home district from the canonical id (agents are sorted by home district)
-__device__ __forceinline__ uint32_t district_of(const DevTables& T, int64_t cid) {
-    int lo = 0, hi = T.D;           // district_start[lo] <= cid < district_start[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(T.district_start + mid) <= cid) lo = mid; else hi = mid;
-    }
-    return (uint32_t)lo;
-}
-// `tile_home` = home district of the tile's first agent: almost always the answer for an away agent
-__device__ __forceinline__ uint32_t home_district(const DevTables& T, uint32_t f, uint32_t a, int64_t cid, int tile_home = -1) {
-    if (!(f & F_AWAY)) return a >> 16;
-    if (tile_home >= 0 && cid < __ldg(T.district_start + tile_home + 1)) return (uint32_t)tile_home;
-    return district_of(T, cid);
-}
 __device__ __forceinline__ int big_slot(const DevTables& T, int64_t cid) {
     int lo = 0, hi = T.n_big;       // big_start[lo] <= cid < big_start[hi]
     while (hi - lo > 1) {
@@ -179,36 +189,40 @@ __device__ __forceinline__ int big_slot(const DevTables& T, int64_t cid) {
     return lo;
 }
 
-__device__ __forceinline__ bool at_own_household(uint32_t f) {
-    const uint32_t kind = (f >> F_LOC_SHIFT) & F_LOC_MASK;
-    return kind == LOC_HOME || (kind == LOC_ECON && ((f >> F_EKIND_SHIFT) & F_EKIND_MASK) == EKIND_HOUSEHOLD);
-}
+__device__ __forceinline__ uint32_t loc_of(uint32_t f) { return (f >> F_LOC_SHIFT) & F_LOC_MASK; }
+__device__ __forceinline__ uint32_t set_loc(uint32_t f, uint32_t loc) { return (f & ~LOCF) | (loc << F_LOC_SHIFT); }
 
 // Outside pool (row of the district x status tables) the agent is currently in, or -1.
 // Hospital is location -current_district (base_model.py:270-272): district 0 maps onto its own outside
 // pool (quirk Q3); every other hospital / the dead location holds no susceptible agent.
-__device__ __forceinline__ int pool_of(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int64_t cid,
-                                       int tile_home = -1) {
-    const uint32_t kind = (f >> F_LOC_SHIFT) & F_LOC_MASK;
-    if (kind == LOC_ECON) {
-        const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
-        if (ek == EKIND_HOME_DISTRICT) return (int)home_district(T, f, a, cid, tile_home);
-        if (ek == EKIND_POOL) return (int)__ldg(G.econ_pool + slot);
-        return -1;
-    }
-    if (kind == LOC_DIST) return (int)(a >> 16);
+__device__ __forceinline__ int pool_of(const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int L0) {
+    const uint32_t kind = loc_of(f);
+    if (kind == LOC_CUR) return (int)(a >> 16);
+    if (kind == LOC_HOMEPOOL) return L0;
+    if (kind == LOC_POOL) return (int)__ldg(G.econ_pool + slot);
     if (kind == LOC_HOSP) return (a >> 16) == 0 ? 0 : -1;
     return -1;
+}
+// location an agent that goes about its economic activity ends up in (base_model.py:331-339, 346-352)
+__device__ __forceinline__ uint32_t econ_loc(uint32_t f) {
+    const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
+    if (ek == EKIND_HOUSEHOLD) return LOC_HOME;
+    if (ek == EKIND_POOL) return LOC_POOL;
+    return (f & F_AWAY) ? LOC_HOMEPOOL : LOC_CUR;
+}
+__device__ __forceinline__ uint32_t rate_index(uint32_t f) {
+    return ((((f >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128u : 0u) + ((f >> F_AGE_SHIFT) & F_AGE_MASK);
 }
 
 // ------------------------------------------------------------------------------------------------ infection event
 // Country.set_epidemic_status for one agent (base_model.py:838-1055).  Returns the new flags; writes the
-// cold vectors; *t_next gets the sub-step at which the first scheduled event fires (>= k_first).
+// cold vectors; the low half of `a` gets the sub-step at which the first scheduled event fires (>= k_first).
+// tally: shared (or global) int array indexed by the enum above.
+template <typename TallyT>
 __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                 int64_t cid, int32_t k_inf, int32_t now_inf, uint32_t k_first,
-                                                 unsigned int* s_tally) {
-    const U4 A4 = agent_draws(T, cid, k_inf, 1u);
-    const U4 B4 = agent_draws(T, cid, k_inf, 2u);
+                                                 int64_t cid, int32_t k_inf, int32_t now_inf, uint32_t k_first, TallyT* tally) {
+    const U4 A4 = agent_draws(T, cid, k_inf, SITE_COURSE_A);
+    const U4 B4 = agent_draws(T, cid, k_inf, SITE_COURSE_B);
     const uint32_t age = (f >> F_AGE_SHIFT) & F_AGE_MASK;
     const uint32_t cur = a >> 16;
     const bool sym = bernoulli(A4.x, T.symptomatic_rate);                                  // :853-857
@@ -229,18 +243,19 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
         else if (crit) t_r = t_o + 21 * DAY;                                                // :996-1000
         else if (hosp) t_r = t_o + 13 * DAY;                                                // :1002-1006
         else t_r = t_o + (int32_t)sample_quantile_u32(T.dwell + 2 * 2 * (ABM_QN + 1), B4.z); // :1008-1022
-        atomicAdd(s_tally + CUM_SYM, 1u);
+        atomicAdd(tally + CUM_SYM, (TallyT)1);
     } else {                                                                                // :1024-1055
         t_o = T_NEVER;
         t_c = now_inf + (int32_t)sample_quantile_u32(T.dwell + 1 * 2 * (ABM_QN + 1), A4.y);
         t_r = t_c + (int32_t)sample_quantile_u32(T.dwell + 3 * 2 * (ABM_QN + 1), B4.z);
-        atomicAdd(s_tally + CUM_ASYM, 1u);
+        atomicAdd(tally + CUM_ASYM, (TallyT)1);
     }
+    atomicAdd(tally + PRE_EXPOSED, (TallyT)1);
     G.t_infected[slot] = now_inf;                                                           // :851
     G.t_contagious[slot] = t_c;
     G.t_onset[slot] = t_o;
     G.t_recovered[slot] = t_r;
-    G.inf_at[slot] = (((f >> F_LOC_SHIFT) & F_LOC_MASK) << 16) | cur;                       // :846-847
+    G.inf_at[slot] = (loc_of(f) << 16) | cur;                                               // :846-847
     f &= ~(F_EPI_MASK | (F_SYM_MASK << F_SYM_SHIFT) | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
     f |= EPI_I | ((sym ? 2u : 1u) << F_SYM_SHIFT) | out;                                    // :850
     // earliest scheduled event (contagious always precedes the others except when onset < 12 h)
@@ -255,31 +270,43 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
 
 // ------------------------------------------------------------------------------------------------ transitions
 // update_agent_states (base_model.py:226-272) + contagious promotion (base_model.py:54-58) for one agent
-// whose next-event index is due.  Cumulative date counters are tallied the first time a date is passed.
+// whose next-event index is due.  Cumulative date counters are tallied the first time a date is passed;
+// the "current" counters of the day log move by the change of epidemic / clinical state.
 __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
-                                                     int32_t now, unsigned int* s_tally) {
+                                                     int32_t now, int* s_tally) {
     const int32_t t_c = G.t_contagious[slot], t_o = G.t_onset[slot], t_r = G.t_recovered[slot];
     const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
     const int32_t t_cs = (f & F_OUT_C) ? t_o + 13 * DAY : T_NEVER;  // hospital end = critical start (base_model.py:953)
     const int32_t t_d = (f & F_OUT_D) ? t_o + 21 * DAY : T_NEVER;   // params.py:177 (== end of critical care when critical)
-    uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = (f >> F_LOC_SHIFT) & F_LOC_MASK;
-    if (t_c < now && epi == EPI_I) atomicAdd(s_tally + CUM_CONTAGIOUS, 1u);
+    const uint32_t epi0 = f & F_EPI_MASK, clin0 = (f >> F_CLIN_SHIFT) & F_CLIN_MASK;
+    uint32_t epi = epi0, clin = clin0, loc = loc_of(f);
+    if (t_c < now && epi == EPI_I) atomicAdd(s_tally + CUM_CONTAGIOUS, 1);
     if (t_d < now && epi < EPI_D) {                                  // :230-237
         epi = EPI_D; loc = LOC_DEAD; clin = 3;
-        atomicAdd(s_tally + CUM_DIED, 1u);
+        atomicAdd(s_tally + CUM_DIED, 1);
     }
     if (t_r < now && epi < EPI_R) {                                  // :240-254
         epi = EPI_R;
         if (t_h < now) loc = LOC_HOME;
         clin = 3;
-        atomicAdd(s_tally + CUM_RECOVERED, 1u);
+        atomicAdd(s_tally + CUM_RECOVERED, 1);
     }
-    if (t_cs < now && clin < 2) { clin = 2; atomicAdd(s_tally + CUM_CRITICAL, 1u); }      // :257-261
-    if (t_h < now && clin < 1) { clin = 1; loc = LOC_HOSP; atomicAdd(s_tally + CUM_HOSPITALIZED, 1u); }  // :263-272
+    if (t_cs < now && clin < 2) { clin = 2; atomicAdd(s_tally + CUM_CRITICAL, 1); }      // :257-261
+    if (t_h < now && clin < 1) { clin = 1; loc = LOC_HOSP; atomicAdd(s_tally + CUM_HOSPITALIZED, 1); }  // :263-272
     if (t_o < now) f |= F_ONSET;                                     // :212-219 (symptom onset passed)
     if (t_c < now && epi < EPI_C) epi = EPI_C;                       // :54-58
-    f = (f & ~(F_EPI_MASK | (F_CLIN_MASK << F_CLIN_SHIFT) | (F_LOC_MASK << F_LOC_SHIFT))) | epi | (clin << F_CLIN_SHIFT) |
-        (loc << F_LOC_SHIFT);
+    if (epi != epi0) {
+        if (epi0 == EPI_I) atomicAdd(s_tally + POST_EXPOSED, -1);
+        if (epi0 == EPI_C) atomicAdd(s_tally + POST_CONTAGIOUS, -1);
+        if (epi == EPI_C) atomicAdd(s_tally + POST_CONTAGIOUS, 1);
+    }
+    if (clin != clin0) {
+        if (clin0 == 1) atomicAdd(s_tally + POST_HOSPITALIZED, -1);
+        if (clin0 == 2) atomicAdd(s_tally + POST_CRITICAL, -1);
+        if (clin == 1) atomicAdd(s_tally + POST_HOSPITALIZED, 1);
+        if (clin == 2) atomicAdd(s_tally + POST_CRITICAL, 1);
+    }
+    f = (f & ~(F_EPI_MASK | (F_CLIN_MASK << F_CLIN_SHIFT) | LOCF)) | epi | (clin << F_CLIN_SHIFT) | (loc << F_LOC_SHIFT);
     uint32_t nf = FIRE_NEVER;
     const int32_t ts[6] = {t_c, t_o, t_h, t_cs, t_d, t_r};
 #pragma unroll
@@ -291,7 +318,7 @@ __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const D
 
 __device__ __forceinline__ bool is_active(uint32_t f, uint32_t a) {
     // get_active_ids (base_model.py:198-209): not hospitalised or recovered, at a non-negative location
-    const uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = (f >> F_LOC_SHIFT) & F_LOC_MASK;
+    const uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = loc_of(f);
     const bool loc_ok = !(loc == LOC_DEAD || (loc == LOC_HOSP && (a >> 16) != 0));
     return (clin < 1 || epi == EPI_R) && loc_ok;
 }
@@ -320,343 +347,349 @@ __device__ __forceinline__ int32_t stay_return_tick(const DevTables& T, uint32_t
 }
 
 // first column j with u < thr[j] of a non-decreasing OD row; none -> column 0 (quirk Q8)   base_model.py:372-377
-__device__ __forceinline__ uint32_t od_destination(const DevTables& T, uint32_t u, int weekday, uint32_t home) {
-    const uint32_t* row = T.od_thr + ((size_t)weekday * T.D + home) * T.D;
-    int lo = 0, hi = T.D;
+__device__ __forceinline__ uint32_t od_destination(const uint32_t* __restrict__ row, int D, uint32_t u) {
+    int lo = 0, hi = D;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (u < __ldg(row + mid)) hi = mid; else lo = mid + 1;
     }
-    return lo < T.D ? (uint32_t)lo : 0u;
+    return lo < D ? (uint32_t)lo : 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
-// One block = one tile of 1024 slots staged in shared memory; one thread owns 4 consecutive slots (one
-// 128-bit load of each hot word).  Work that only a few agents need in a given sub-step (the infection
-// draw at night, the disease-course sampling, due transitions, length-of-stay sampling) is not executed
-// in place -- a warp would run it for one or two active lanes -- but appended to per-tile queues in
-// shared memory and then processed with all lanes busy.  MODE is the compile-time copy of StepArgs.mode
-// for the four sub-step kinds that make up a simulated day (RUNTIME_MODE = read it from the argument).
 constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
-constexpr int Q_DRAW = 0, Q_INFECT = 1, Q_TRANS = 2, Q_STAY = 3, N_QUEUES = 4;
 
-__device__ __forceinline__ void enqueue_one(unsigned int* s_n, uint16_t* s_q, int q, int o) {
-    const unsigned int pos = atomicAdd(s_n + q, 1u);
-    s_q[q * ABM_TILE + pos] = (uint16_t)o;
-}
+// iterate `BODY` over the agents whose bit is set in the per-lane `mask`; inside, J is the agent's
+// index 0..3 within the lane and fj / aj are its (mutable) flags / aux words
+#define ABM_FUNNEL(mask, ...)                                                        \
+    while (__any_sync(FULL, (mask) != 0u)) {                                         \
+        if (mask) {                                                                  \
+            const int J = __ffs(mask) - 1;                                           \
+            (mask) &= (mask) - 1u;                                                   \
+            uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));          \
+            uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));          \
+            const uint32_t fj_in = fj, aj_in = aj;                                   \
+            __VA_ARGS__                                                              \
+            if (fj != fj_in) { dirty_f = true; if (J == 0) f0 = fj; else if (J == 1) f1 = fj; else if (J == 2) f2 = fj; else f3 = fj; } \
+            if (aj != aj_in) { dirty_a = true; if (J == 0) a0 = aj; else if (J == 1) a1 = aj; else if (J == 2) a2 = aj; else a3 = aj; } \
+        }                                                                            \
+    }
 
 template <uint32_t MODE>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS)
 abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
-    __shared__ __align__(16) uint32_t s_f[ABM_TILE];     // staged flags
-    __shared__ __align__(16) uint32_t s_a[ABM_TILE];     // staged aux
-    __shared__ __align__(16) uint32_t s_thr[ABM_TILE];   // infection threshold per slot; later the stay draw
-    __shared__ uint16_t s_q[N_QUEUES * ABM_TILE];
-    __shared__ unsigned int s_n[N_QUEUES];
-    __shared__ unsigned int s_tally[N_TALLY];
-    __shared__ unsigned int s_cnt[ABM_MAX_STATUS];
-    __shared__ unsigned int s_rlo[ABM_MAX_STATUS], s_rhi[ABM_MAX_STATUS];
+    __shared__ uint32_t s_hz[WARPS][2][SUB];          // per-warp household hazard sums (low / high 16-bit parts)
+    __shared__ int s_tally[N_TALLY];
+    __shared__ unsigned int s_cnt[ABM_MAX_STATUS], s_rlo[ABM_MAX_STATUS], s_rhi[ABM_MAX_STATUS];
 
     const uint32_t mode = MODE == RUNTIME_MODE ? s.mode : ((MODE & ~M_WEEKDAY) | (s.mode & M_WEEKDAY));
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t tile = blockIdx.x;
-    const int o0 = tid * PER_THREAD;
-    const int64_t slot0 = tile * ABM_TILE + o0;
-    const int64_t cid_tile = __ldg(T.tile_base + tile);
-    const int L0 = (int)__ldg(T.tile_home + tile);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < N_TALLY) s_tally[tid] = 0;
+    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_rlo[tid] = 0; s_rhi[tid] = 0; }
+    __syncthreads();
+
+    const int64_t sub = (int64_t)blockIdx.x * WARPS + wid;
+    const unsigned long long info = __ldg(T.sub_info + sub);
+    const int L0 = (int)(info >> 48);                                        // home district of every agent here
+    const int L0c = (int)(__ldg(T.sub_info + (int64_t)blockIdx.x * WARPS) >> 48);   // district of the CTA-level accumulators
+    const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;     // canonical id of this lane's first slot
+    const int64_t slot0 = sub * SUB + lane * PER_LANE;
+    const int A = T.A;
 
     const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
     const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
-    uint32_t f[PER_THREAD] = {f4.x, f4.y, f4.z, f4.w};
-    uint32_t a[PER_THREAD] = {a4.x, a4.y, a4.z, a4.w};
+    uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
+    uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
+    bool dirty_f = false, dirty_a = false;
+    uint32_t* hz_lo = s_hz[wid][0];
+    uint32_t* hz_hi = s_hz[wid][1];
 
-    if (tid < N_TALLY) s_tally[tid] = 0;
-    if (tid < N_QUEUES) s_n[tid] = 0;
-    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_rlo[tid] = 0; s_rhi[tid] = 0; }
-    *reinterpret_cast<uint4*>(s_f + o0) = f4;
-    *reinterpret_cast<uint4*>(s_a + o0) = a4;
-    *reinterpret_cast<uint4*>(s_thr + o0) = make_uint4(0u, 0u, 0u, 0u);
-
-    // ---------------------------------------------------------------- household thresholds for I(k-1)
-    int tile_has_cont_home = 0;
+    // ================================================================ I(k-1): infection draws
     if (mode & M_INFECT) {
-        bool any_cont_home = false;
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j)
-            any_cont_home |= (f[j] & (F_EPI_MASK | F_BIGHH)) == EPI_C && at_own_household(f[j]);
-        tile_has_cont_home = __syncthreads_or(any_cont_home);
-        if (tile_has_cont_home) {
-            // every household head sums the log-survival increments of its contagious members present
-            // (1 - prod(1 - 3 r_i), base_model.py:156-175, 184-187) and publishes the threshold to all members
-#pragma unroll 1
-            for (int j = 0; j < PER_THREAD; ++j) {
-                const int o = o0 + j;
-                uint32_t c = s_f[o];
-                if ((c & (F_HEAD | F_BIGHH | F_FILLER)) != F_HEAD) continue;
-                int e = o;
-                unsigned long long hsum = 0ull;
-                const uint32_t* q = T.qfx;
-                if (T.hw_rows > 1) q += (size_t)home_district(T, c, s_a[o], cid_tile + o, L0) * 256;
-                do {
-                    if ((c & F_EPI_MASK) == EPI_C && at_own_household(c))
-                        hsum += __ldg(q + ((((c >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((c >> F_AGE_SHIFT) & F_AGE_MASK));
-                    ++e;
-                    if (e >= ABM_TILE) break;
-                    c = s_f[e];
-                } while (!(c & F_HEAD));
-                if (hsum) {
-                    const uint32_t thr = hazard_threshold(__dmul_rn((double)hsum, 1.0 / 4294967296.0));
-                    for (int m = o; m < e; ++m) s_thr[m] = thr;
-                }
-            }
-            __syncthreads();
-        }
-    } else {
-        __syncthreads();
-    }
-
-    // ---------------------------------------------------------------- P1: classify own agents, build the queues
-    uint32_t logc = 0;     // packed "current" counters for the day log (state after I(k-1), before T(k))
-    {
-        int n_draw = 0;
-        uint32_t draw_mask = 0;
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const uint32_t fj = f[j], aj = a[j];
-            const int o = o0 + j;
-            if ((mode & M_INFECT) && (fj & F_EPI_MASK) == EPI_S) {
+        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;      // 31-bit infection thresholds of the four agents
+        // ---- household term: 1 - prod(1 - 3 r_i) over contagious members present (base_model.py:156-175, 184-187)
+        constexpr uint32_t CH_MASK = F_EPI_MASK | LOCF | F_BIGHH, CH_VAL = EPI_C | (LOC_HOME << F_LOC_SHIFT);
+        const bool c0 = (f0 & CH_MASK) == CH_VAL, c1 = (f1 & CH_MASK) == CH_VAL, c2 = (f2 & CH_MASK) == CH_VAL,
+                   c3 = (f3 & CH_MASK) == CH_VAL;
+        if (__any_sync(FULL, c0 | c1 | c2 | c3)) {
+            // index of each slot's household within the sub-tile = number of household heads up to it - 1
+            const uint32_t h0 = (f0 >> 23) & 1u, h1 = (f1 >> 23) & 1u, h2 = (f2 >> 23) & 1u, h3 = (f3 >> 23) & 1u;
+            const uint32_t B0 = __ballot_sync(FULL, h0), B1 = __ballot_sync(FULL, h1), B2 = __ballot_sync(FULL, h2),
+                           B3 = __ballot_sync(FULL, h3);
+            const uint32_t lt = (1u << lane) - 1u;
+            const int before = __popc(B0 & lt) + __popc(B1 & lt) + __popc(B2 & lt) + __popc(B3 & lt) - 1;
+            const int i0 = before + (int)h0, i1 = i0 + (int)h1, i2 = i1 + (int)h2, i3 = i2 + (int)h3;
+            const int n_hh = __popc(B0) + __popc(B1) + __popc(B2) + __popc(B3);
+            *reinterpret_cast<uint4*>(hz_lo + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(hz_hi + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            const uint32_t* q = T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0);
+            if (c0) { const uint32_t v = __ldg(q + rate_index(f0)); atomicAdd(hz_lo + i0, v & 0xFFFFu); atomicAdd(hz_hi + i0, v >> 16); }
+            if (c1) { const uint32_t v = __ldg(q + rate_index(f1)); atomicAdd(hz_lo + i1, v & 0xFFFFu); atomicAdd(hz_hi + i1, v >> 16); }
+            if (c2) { const uint32_t v = __ldg(q + rate_index(f2)); atomicAdd(hz_lo + i2, v & 0xFFFFu); atomicAdd(hz_hi + i2, v >> 16); }
+            if (c3) { const uint32_t v = __ldg(q + rate_index(f3)); atomicAdd(hz_lo + i3, v & 0xFFFFu); atomicAdd(hz_hi + i3, v >> 16); }
+            __syncwarp();
+            for (int h = lane; h < n_hh; h += 32) {   // one threshold per exposed household
+                const uint32_t lo = hz_lo[h], hi = hz_hi[h];
                 uint32_t thr = 0;
-                if (at_own_household(fj)) {
-                    if (fj & F_BIGHH) {
-                        const unsigned long long hz = Wk.hbig_read[big_slot(T, cid_tile + o)];
-                        if (hz) { thr = hazard_threshold(__dmul_rn((double)hz, 1.0 / 4294967296.0)); s_thr[o] = thr; }
-                    } else if (tile_has_cont_home) {
-                        thr = s_thr[o];
-                    }
-                } else {
-                    const int pool = pool_of(T, G, fj, aj, slot0 + j, cid_tile + o, L0);
-                    if (pool >= 0) {
-                        thr = __ldg(Wk.thr_out + pool * T.A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
-                        if (thr) s_thr[o] = thr;
-                    }
+                if (lo | hi) {
+                    const unsigned long long hs = ((unsigned long long)hi << 16) + lo;
+                    thr = hazard_threshold(__dmul_rn((double)hs, 1.0 / 4294967296.0));
                 }
-                if (thr) { draw_mask |= 1u << j; ++n_draw; }
+                hz_lo[h] = thr;
             }
-            if (mode & M_STEP) {
-                if (mode & M_LOG) {
-                    const uint32_t epi = fj & F_EPI_MASK, clin = (fj >> F_CLIN_SHIFT) & F_CLIN_MASK;
-                    logc += (epi == EPI_I ? 1u : 0u) | (epi == EPI_C ? 0x100u : 0u) | (clin == 1 ? 0x10000u : 0u) | (clin == 2 ? 0x1000000u : 0u);
+            __syncwarp();
+            constexpr uint32_t SH_VAL = EPI_S | (LOC_HOME << F_LOC_SHIFT);
+            if ((f0 & CH_MASK) == SH_VAL) t0 = hz_lo[i0];
+            if ((f1 & CH_MASK) == SH_VAL) t1 = hz_lo[i1];
+            if ((f2 & CH_MASK) == SH_VAL) t2 = hz_lo[i2];
+            if ((f3 & CH_MASK) == SH_VAL) t3 = hz_lo[i3];
+        }
+        // ---- outside pools and big households
+        {
+            // susceptible and not (at home in a small household): loc != HOME, or BIGHH
+            const bool o0 = (f0 & F_EPI_MASK) == EPI_S && ((f0 & (LOCF | F_BIGHH)) != 0u);
+            const bool o1 = (f1 & F_EPI_MASK) == EPI_S && ((f1 & (LOCF | F_BIGHH)) != 0u);
+            const bool o2 = (f2 & F_EPI_MASK) == EPI_S && ((f2 & (LOCF | F_BIGHH)) != 0u);
+            const bool o3 = (f3 & F_EPI_MASK) == EPI_S && ((f3 & (LOCF | F_BIGHH)) != 0u);
+            if (__any_sync(FULL, o0 | o1 | o2 | o3)) {
+                const uint32_t row_thr = lane < A ? __ldg(Wk.thr_out + L0 * A + lane) : 0u;
+                const uint32_t r0 = __shfl_sync(FULL, row_thr, (f0 >> F_STATUS_SHIFT) & F_STATUS_MASK);
+                const uint32_t r1 = __shfl_sync(FULL, row_thr, (f1 >> F_STATUS_SHIFT) & F_STATUS_MASK);
+                const uint32_t r2 = __shfl_sync(FULL, row_thr, (f2 >> F_STATUS_SHIFT) & F_STATUS_MASK);
+                const uint32_t r3 = __shfl_sync(FULL, row_thr, (f3 >> F_STATUS_SHIFT) & F_STATUS_MASK);
+                uint32_t odd = 0;     // agents in another pool than the home one, or in a big household
+#define ABM_OUT_THR(fj, aj, oj, rj, tj, bit)                                                        \
+                if (oj) {                                                                           \
+                    const uint32_t kind = loc_of(fj);                                               \
+                    if (kind == LOC_HOMEPOOL || (kind == LOC_CUR && (int)((aj) >> 16) == L0)) tj = rj; \
+                    else odd |= (bit);                                                              \
                 }
-                if ((aj & 0xFFFFu) <= (uint32_t)s.k) enqueue_one(s_n, s_q, Q_TRANS, o);
+                ABM_OUT_THR(f0, a0, o0, r0, t0, 1u)
+                ABM_OUT_THR(f1, a1, o1, r1, t1, 2u)
+                ABM_OUT_THR(f2, a2, o2, r2, t2, 4u)
+                ABM_OUT_THR(f3, a3, o3, r3, t3, 8u)
+#undef ABM_OUT_THR
+                ABM_FUNNEL(odd, {
+                    uint32_t thr = 0;
+                    if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
+                        const unsigned long long hzv = Wk.hbig_read[big_slot(T, cid0 + J)];
+                        if (hzv) thr = hazard_threshold(__dmul_rn((double)hzv, 1.0 / 4294967296.0));
+                    } else {
+                        const int pool = pool_of(G, fj, aj, slot0 + J, L0);
+                        if (pool >= 0) thr = __ldg(Wk.thr_out + pool * A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
+                    }
+                    if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
+                })
             }
         }
-        if (mode & M_INFECT) {
-            // warp-aggregated append of the draw queue
-            int incl = n_draw;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            int base = 0;
-            if (lane == 31 && total) base = (int)atomicAdd(s_n + Q_DRAW, (unsigned int)total);
-            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - n_draw;
-#pragma unroll
-            for (int j = 0; j < PER_THREAD; ++j)
-                if (draw_mask & (1u << j)) s_q[Q_DRAW * ABM_TILE + base++] = (uint16_t)(o0 + j);
+        // ---- the draw: one Philox block for the four agents of the lane
+        uint32_t newly = 0;
+        if (t0 | t1 | t2 | t3) {
+            const U4 X = group_draws(T, cid0, s.k_inf, SITE_INFECT);
+            newly = ((X.x >> 1) < t0 ? 1u : 0u) | ((X.y >> 1) < t1 ? 2u : 0u) | ((X.z >> 1) < t2 ? 4u : 0u) |
+                    ((X.w >> 1) < t3 ? 8u : 0u);
         }
-    }
-    __syncthreads();
-
-    if (mode & M_INFECT) {
-        // ------------------------------------------------------------ P2: the infection draws, all lanes busy
-        const int n_draw = (int)s_n[Q_DRAW];
-        for (int i = tid; i < n_draw; i += THREADS) {
-            const int o = s_q[Q_DRAW * ABM_TILE + i];
-            const U4 X = agent_draws(T, cid_tile + o, s.k_inf, 0u);
-            if ((X.x >> 1) < s_thr[o]) enqueue_one(s_n, s_q, Q_INFECT, o);
-        }
-        __syncthreads();
-        // ------------------------------------------------------------ P3: disease course of the newly infected
-        const int n_inf = (int)s_n[Q_INFECT];
-        for (int i = tid; i < n_inf; i += THREADS) {
-            const int o = s_q[Q_INFECT * ABM_TILE + i];
-            const int64_t slot = tile * ABM_TILE + o;
-            uint32_t aj = s_a[o];
-            const uint32_t fj = infect_agent(T, G, s_f[o], aj, slot, cid_tile + o, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
-            s_f[o] = fj; s_a[o] = aj;
-            G.flags[slot] = fj; G.aux[slot] = aj;
-            atomicAdd(s_tally + CUM_INFECTED, 1u);
-            if (mode & M_STEP) {
-                if (mode & M_LOG) atomicAdd(s_tally + CUR_EXPOSED, 1u);
-                if ((aj & 0xFFFFu) <= (uint32_t)s.k) enqueue_one(s_n, s_q, Q_TRANS, o);
-            }
-        }
-        if (mode & M_STEP) __syncthreads();
+        // ---- disease course of the newly infected
+        ABM_FUNNEL(newly, {
+            fj = infect_agent(T, G, fj, aj, slot0 + J, cid0 + J, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+            atomicAdd(s_tally + CUM_INFECTED, 1);
+        })
     }
 
     if (mode & M_STEP) {
-        // ------------------------------------------------------------ T(k): due transitions
-        const int n_trans = (int)s_n[Q_TRANS];
-        if (n_trans) {
-            for (int i = tid; i < n_trans; i += THREADS) {
-                const int o = s_q[Q_TRANS * ABM_TILE + i];
-                const int64_t slot = tile * ABM_TILE + o;
-                uint32_t aj = s_a[o];
-                const uint32_t fj = transition_agent(T, G, s_f[o], aj, slot, s.now, s_tally);
-                s_f[o] = fj; s_a[o] = aj;
-                G.flags[slot] = fj; G.aux[slot] = aj;
-            }
+        // ============================================================ T(k): due transitions
+        {
+            const uint32_t k = (uint32_t)s.k;
+            uint32_t due = ((a0 & 0xFFFFu) <= k ? 1u : 0u) | ((a1 & 0xFFFFu) <= k ? 2u : 0u) | ((a2 & 0xFFFFu) <= k ? 4u : 0u) |
+                           ((a3 & 0xFFFFu) <= k ? 8u : 0u);
+            ABM_FUNNEL(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
         }
-        if (n_trans || (s_n[Q_INFECT] && (mode & M_INFECT))) {
-            __syncthreads();
-            const uint4 nf = *reinterpret_cast<const uint4*>(s_f + o0);
-            const uint4 na = *reinterpret_cast<const uint4*>(s_a + o0);
-            f[0] = nf.x; f[1] = nf.y; f[2] = nf.z; f[3] = nf.w;
-            a[0] = na.x; a[1] = na.y; a[2] = na.z; a[3] = na.w;
-        }
-        const uint32_t fb[PER_THREAD] = {f[0], f[1], f[2], f[3]};   // what global memory holds now
-        const uint32_t ab[PER_THREAD] = {a[0], a[1], a[2], a[3]};
 
-        // ------------------------------------------------------------ M(k): movement (base_model.py:274-441)
-        if (mode & (M_GO_OUT | M_GO_HOME)) {
-#pragma unroll
-            for (int j = 0; j < PER_THREAD; ++j) {
-                uint32_t fj = f[j], aj = a[j];
-                if ((fj & F_FILLER) || !is_active(fj, aj)) continue;
-                const int o = o0 + j;
-                const int64_t slot = slot0 + j, cid = cid_tile + o;
-                if (mode & M_GO_HOME) {                                                    // :274-302
-                    if (!(fj & F_AWAY)) {
-                        fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_HOME << F_LOC_SHIFT);
-                    } else if (G.t_return[slot] < s.now) {
-                        aj = (aj & 0xFFFFu) | (home_district(T, fj, aj, cid, L0) << 16);
-                        fj = (fj & ~(F_AWAY | (F_LOC_MASK << F_LOC_SHIFT))) | (LOC_HOME << F_LOC_SHIFT);
+        // ============================================================ M(k): movement (base_model.py:274-441)
+        if (mode & M_GO_HOME) {                                                         // :274-302
+            uint32_t away = 0;
+#define ABM_GO_HOME(fj, aj, bit)                                                                     \
+            if (is_active(fj, aj)) {                                                                 \
+                if (!((fj) & F_AWAY)) { const uint32_t nf = set_loc(fj, LOC_HOME); dirty_f |= nf != (fj); fj = nf; } \
+                else away |= (bit);                                                                  \
+            }
+            ABM_GO_HOME(f0, a0, 1u)
+            ABM_GO_HOME(f1, a1, 2u)
+            ABM_GO_HOME(f2, a2, 4u)
+            ABM_GO_HOME(f3, a3, 8u)
+#undef ABM_GO_HOME
+            ABM_FUNNEL(away, {
+                if (G.t_return[slot0 + J] < s.now) {                                    // :285-293
+                    aj = (aj & 0xFFFFu) | ((uint32_t)L0 << 16);
+                    fj = set_loc(fj & ~F_AWAY, LOC_HOME);
+                }
+            })
+        }
+        if (mode & M_GO_OUT) {                                                          // :304-340
+            const uint2 mc = *reinterpret_cast<const uint2*>(G.move_class + slot0);
+            const int col = (mode & M_WEEKDAY) ? 0 : 2;
+            const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
+            const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
+            const U4 XM = group_draws(T, cid0, s.k, SITE_MOVER);
+            uint32_t mover = 0, want_od = 0;
+#define ABM_MOVER(fj, aj, cls, xm, bit)                                                              \
+            if (is_active(fj, aj)) {                                                                 \
+                const bool mild = T.mild_active && ((fj) & F_ONSET) && ((fj) & F_EPI_MASK) < EPI_R;   /* :212-219, :316 */ \
+                const uint32_t thr = __ldg(T.move_thr + 4u * (cls) + col + (mild ? 1 : 0));           \
+                if (((xm) >> 1) < thr) {                                                /* :317-318 a mover */ \
+                    mover |= (bit);                                                                  \
+                    if ((fj) & F_DMOVER) want_od |= (bit);                                           \
+                }                                                                                    \
+            }
+            ABM_MOVER(f0, a0, mc.x & 0xFFFFu, XM.x, 1u)
+            ABM_MOVER(f1, a1, mc.x >> 16, XM.y, 2u)
+            ABM_MOVER(f2, a2, mc.y & 0xFFFFu, XM.z, 4u)
+            ABM_MOVER(f3, a3, mc.y >> 16, XM.w, 8u)
+#undef ABM_MOVER
+            // district movers at home whose OD draw falls in the stay-home interval of their row, and movers
+            // that are neither away nor district movers, just go about their economic activity
+            uint32_t trav = 0;        // away agents and agents whose draw leaves the home district
+            U4 XO = U4{0u, 0u, 0u, 0u};
+            if (want_od) XO = group_draws(T, cid0, s.k, SITE_OD);
+#define ABM_GO_OUT(fj, xo, bit)                                                                      \
+            if (mover & (bit)) {                                                                     \
+                const uint32_t u = (xo) >> 1;                                                        \
+                if (((fj) & F_AWAY) || (((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi))) trav |= (bit); \
+                else { const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty_f |= nf != (fj); fj = nf; } \
+            }
+            ABM_GO_OUT(f0, XO.x, 1u)
+            ABM_GO_OUT(f1, XO.y, 2u)
+            ABM_GO_OUT(f2, XO.z, 4u)
+            ABM_GO_OUT(f3, XO.w, 8u)
+#undef ABM_GO_OUT
+            ABM_FUNNEL(trav, {
+                if ((fj & F_AWAY) && G.t_return[slot0 + J] < s.now) {                   // :342-360 back in the home district
+                    aj = (aj & 0xFFFFu) | ((uint32_t)L0 << 16);
+                    fj &= ~F_AWAY;
+                }
+                bool left = false;
+                if ((fj & F_DMOVER) && !(fj & F_AWAY)) {                                // :366-370
+                    const uint32_t dest = od_destination(od_row, T.D, word_of(XO, J) >> 1);
+                    if (dest != (uint32_t)L0) {                                         // :410-439
+                        const U4 XS = group_draws(T, cid0, s.k, SITE_STAY);
+                        G.t_return[slot0 + J] = stay_return_tick(T, word_of(XS, J), s.weekday, (uint32_t)L0, dest, s.now);
+                        fj = set_loc(fj, LOC_CUR) | F_AWAY;
+                        aj = (aj & 0xFFFFu) | (dest << 16);
+                        left = true;
                     }
                 }
-                if (mode & M_GO_OUT) {                                                     // :304-340
-                    const bool mild = T.mild_active && (fj & F_ONSET) && (fj & F_EPI_MASK) < EPI_R;   // :212-219, :316
-                    const uint32_t thr = __ldg(T.move_thr + 4 * (uint32_t)__ldg(G.move_class + slot) + ((mode & M_WEEKDAY) ? 0 : 2) + (mild ? 1 : 0));
-                    if (thr) {
-                        const bool needs_od = (fj & F_DMOVER) != 0;
-                        U4 X = U4{0, 0, 0, 0};
-                        if (thr < 0x80000000u || needs_od) X = agent_draws(T, cid, s.k, 0u);
-                        if ((X.y >> 1) < thr) {                                            // :317-318 a mover
-                            if ((fj & F_AWAY) && G.t_return[slot] < s.now) {               // :342-360
-                                aj = (aj & 0xFFFFu) | (home_district(T, fj, aj, cid, L0) << 16);
-                                fj &= ~F_AWAY;
-                            }
-                            bool left = false;
-                            if (needs_od && !(fj & F_AWAY)) {                              // :366-370
-                                const uint32_t home = aj >> 16;
-                                const uint32_t dest = od_destination(T, X.z >> 1, s.weekday, home);
-                                if (dest != home) {                                        // :410-439
-                                    fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | F_AWAY | (LOC_DIST << F_LOC_SHIFT);
-                                    aj = (aj & 0xFFFFu) | (dest << 16);
-                                    s_thr[o] = X.w;            // the stay draw, consumed by the Q_STAY pass
-                                    s_a[o] = (home << 16) | dest;
-                                    enqueue_one(s_n, s_q, Q_STAY, o);
-                                    left = true;
-                                }
-                            }
-                            if (!left) fj = (fj & ~(F_LOC_MASK << F_LOC_SHIFT)) | (LOC_ECON << F_LOC_SHIFT);   // :331-339, :346-352
-                        }
+                if (!left) fj = set_loc(fj, econ_loc(fj));                              // :331-339, :346-352
+            })
+        }
+
+        // ============================================================ A(k): pressure / headcount tables
+        unsigned long long* acc_r = Wk.acc;
+        unsigned long long* acc_n = Wk.acc + (size_t)T.P * A;
+        const bool cta_acc = L0 == L0c;      // this warp may use the CTA-level shared accumulators
+        uint32_t work = 0;                   // agents whose table contribution goes through the funnel
+        if (mode & M_DENSE) {
+            // most agents are in the outside pool of their home district: per-lane head counts in 4-bit
+            // fields (status 0..11), widened to bytes for three warp reductions
+            unsigned long long cw = 0ull;
+#define ABM_COUNT(fj, aj, bit)                                                                       \
+            {                                                                                        \
+                const uint32_t kind = loc_of(fj);                                                    \
+                const bool in_home_pool = kind == LOC_HOMEPOOL || (kind == LOC_CUR && (int)((aj) >> 16) == L0); \
+                const bool elsewhere = (kind == LOC_CUR && !in_home_pool) || kind == LOC_POOL || (kind == LOC_HOSP && ((aj) >> 16) == 0u); \
+                if (in_home_pool) cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);            \
+                const bool cont = ((fj) & F_EPI_MASK) == EPI_C;                                      \
+                if (elsewhere || (cont && (in_home_pool || (((fj) & (LOCF | F_BIGHH)) == F_BIGHH)))) work |= (bit); \
+            }
+            ABM_COUNT(f0, a0, 1u)
+            ABM_COUNT(f1, a1, 2u)
+            ABM_COUNT(f2, a2, 4u)
+            ABM_COUNT(f3, a3, 8u)
+#undef ABM_COUNT
+            const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
+            const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
+            const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
+            const uint32_t hi = __reduce_add_sync(FULL, (hi32 & 0x0F0Fu) | (((hi32 >> 4) & 0x0F0Fu) << 16));   // 8,10 | 9,11
+            if (lane < A) {
+                const uint32_t w = lane < 8 ? ((lane & 1) ? od : ev) : hi;
+                const uint32_t sh = lane < 8 ? 8u * (lane >> 1) : 8u * (((lane - 8) >> 1) + 2 * ((lane - 8) & 1));
+                const unsigned int v = (w >> sh) & 0xFFu;
+                if (v) {
+                    if (cta_acc) atomicAdd(s_cnt + lane, v);
+                    else atomicAdd(acc_n + (size_t)L0 * A + lane, (unsigned long long)v);
+                }
+            }
+        } else {
+#define ABM_SPARSE(fj, aj, bit)                                                                      \
+            {                                                                                        \
+                const uint32_t kind = loc_of(fj);                                                    \
+                const bool pooled = kind == LOC_CUR || kind == LOC_HOMEPOOL || kind == LOC_POOL || (kind == LOC_HOSP && ((aj) >> 16) == 0u); \
+                if (pooled || (((fj) & (F_EPI_MASK | LOCF | F_BIGHH)) == (EPI_C | F_BIGHH))) work |= (bit); \
+            }
+            ABM_SPARSE(f0, a0, 1u)
+            ABM_SPARSE(f1, a1, 2u)
+            ABM_SPARSE(f2, a2, 4u)
+            ABM_SPARSE(f3, a3, 8u)
+#undef ABM_SPARSE
+        }
+        {
+            const bool dense = (mode & M_DENSE) != 0;
+            ABM_FUNNEL(work, {
+                const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
+                const bool cont = (fj & F_EPI_MASK) == EPI_C;
+                const int pool = pool_of(G, fj, aj, slot0 + J, L0);
+                if (pool >= 0) {
+                    const uint32_t kind = loc_of(fj);
+                    const bool counted = dense && (kind == LOC_HOMEPOOL || (kind == LOC_CUR && pool == L0));
+                    const uint32_t r = cont ? __ldg(T.rfx + rate_index(fj)) : 0u;
+                    if (pool == L0 && cta_acc) {
+                        if (!counted) atomicAdd(s_cnt + st, 1u);
+                        if (cont) { atomicAdd(s_rlo + st, r & 0xFFFFu); atomicAdd(s_rhi + st, r >> 16); }
+                    } else {
+                        if (!counted) atomicAdd(acc_n + (size_t)pool * A + st, 1ull);
+                        if (cont) atomicAdd(acc_r + (size_t)pool * A + st, (unsigned long long)r);
                     }
+                } else if (cont && (fj & F_BIGHH) && loc_of(fj) == LOC_HOME) {
+                    const uint32_t qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0) + rate_index(fj));
+                    atomicAdd(Wk.hbig_write + big_slot(T, cid0 + J), (unsigned long long)qv);
                 }
-                f[j] = fj; a[j] = aj;
-            }
-        }
-
-        // ------------------------------------------------------------ A(k): pressure / headcount tables
-        uint32_t cw0 = 0, cw1 = 0, cw2 = 0;    // packed per-status head counts of this thread (8 bits each)
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const uint32_t fj = f[j], aj = a[j];
-            const int64_t slot = slot0 + j, cid = cid_tile + o0 + j;
-            const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
-            const int pool = pool_of(T, G, fj, aj, slot, cid, L0);
-            const bool cont = (fj & F_EPI_MASK) == EPI_C;
-            if (pool >= 0) {
-                const uint32_t r = cont ? __ldg(T.rfx + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK)) : 0u;
-                if (pool == L0) {
-                    const uint32_t inc = 1u << (8 * (st & 3));
-                    if ((st >> 2) == 0) cw0 += inc; else if ((st >> 2) == 1) cw1 += inc; else cw2 += inc;
-                    if (cont) { atomicAdd(s_rlo + st, r & 0xFFFFu); atomicAdd(s_rhi + st, r >> 16); }
-                } else {
-                    atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)pool * T.A + st, 1ull);
-                    if (cont) atomicAdd(Wk.acc + (size_t)pool * T.A + st, (unsigned long long)r);
-                }
-            } else if (cont && (fj & F_BIGHH) && at_own_household(fj)) {
-                const uint32_t qrow = T.hw_rows > 1 ? home_district(T, fj, aj, cid, L0) : 0u;
-                const uint32_t q = __ldg(T.qfx + (size_t)qrow * 256 + ((((fj >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128 : 0) + ((fj >> F_AGE_SHIFT) & F_AGE_MASK));
-                atomicAdd(Wk.hbig_write + big_slot(T, cid), (unsigned long long)q);
-            }
-        }
-
-        // ------------------------------------------------------------ write back what movement changed
-        if (f[0] != fb[0] || f[1] != fb[1] || f[2] != fb[2] || f[3] != fb[3])
-            *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f[0], f[1], f[2], f[3]);
-        if (a[0] != ab[0] || a[1] != ab[1] || a[2] != ab[2] || a[3] != ab[3])
-            *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a[0], a[1], a[2], a[3]);
-
-        if (mode & M_LOG) {
-            logc = __reduce_add_sync(0xFFFFFFFFu, logc);   // <= 128 per 8-bit field
-            if (lane < 4) {
-                const unsigned int v = (logc >> (8 * lane)) & 0xFFu;
-                if (v) atomicAdd(s_tally + CUR_EXPOSED + lane, v);
-            }
-        }
-        // head counts: 3 packed warp reductions, lane b keeps status b
-        const uint32_t w0 = __reduce_add_sync(0xFFFFFFFFu, cw0);
-        const uint32_t w1 = __reduce_add_sync(0xFFFFFFFFu, cw1);
-        const uint32_t w2 = __reduce_add_sync(0xFFFFFFFFu, cw2);
-        if (lane < T.A) {
-            const uint32_t w = (lane >> 2) == 0 ? w0 : ((lane >> 2) == 1 ? w1 : w2);
-            const unsigned int v = (w >> (8 * (lane & 3))) & 0xFFu;
-            if (v) atomicAdd(s_cnt + lane, v);
+            })
         }
     }
+
+    // ================================================================ write back what changed
+    if (dirty_f) *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
+    if (dirty_a) *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
+
     __syncthreads();
-    if (mode & M_GO_OUT) {
-        // ------------------------------------------------------------ length of stay of the departing travellers
-        const int n_stay = (int)s_n[Q_STAY];
-        for (int i = tid; i < n_stay; i += THREADS) {
-            const int o = s_q[Q_STAY * ABM_TILE + i];
-            const uint32_t hd = s_a[o];
-            G.t_return[tile * ABM_TILE + o] = stay_return_tick(T, s_thr[o], s.weekday, hd >> 16, hd & 0xFFFFu, s.now);
-        }
-    }
     if (tid < N_TALLY) {
-        const unsigned int v = s_tally[tid];
-        if (v) {
-            if (tid < CUR_EXPOSED) atomicAdd(Wk.cum + tid, (unsigned long long)v);
-            else atomicAdd(reinterpret_cast<unsigned long long*>(Wk.log_row) + (ABM_C_CURRENT_EXPOSED_CASES + tid - CUR_EXPOSED),
-                           (unsigned long long)v);
-        }
+        const int v = s_tally[tid];
+        if (v) atomicAdd(Wk.tally + tid, (unsigned long long)(long long)v);
     }
-    if ((mode & M_STEP) && tid >= 32 && tid < 32 + T.A) {
+    if ((mode & M_STEP) && tid >= 32 && tid < 32 + A) {
         const int b = tid - 32;
-        if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * T.A + (size_t)L0 * T.A + b, (unsigned long long)s_cnt[b]);
+        if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * A + (size_t)L0c * A + b, (unsigned long long)s_cnt[b]);
         const unsigned long long r = ((unsigned long long)s_rhi[b] << 16) + s_rlo[b];
-        if (r) atomicAdd(Wk.acc + (size_t)L0 * T.A + b, r);
+        if (r) atomicAdd(Wk.acc + (size_t)L0c * A + b, r);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ table kernel
 // District x status tables -> infection thresholds:
 //   lambda[L][b] = hw[L] * (sum_a W[a][b] * R[L][a]) / Ncnt[L][b],  thr = ceil((1 - exp(-lambda)) * 2^31)
-// then clears the accumulators for the next sub-step, snapshots them for inspection, and at log
-// sub-steps copies the cumulative counters into the day-log row.
+// from the tables of the sub-step just executed; clears the other table buffer (used by the next
+// sub-step), folds the per-launch tallies into the running counters and, at log sub-steps, writes the
+// day-log row: cumulative date counters include this sub-step's transitions, the "current" counters are
+// taken before them (base_model.py:36-38: log_model_output runs before update_agent_states).
 struct TableArgs {
     int32_t write_log;
     int32_t tick;
     long long seeds_before_now;
 };
 
-__global__ void abm_hazard_table_kernel(const DevTables T, unsigned long long* acc, unsigned long long* acc_snapshot,
-                                        uint32_t* thr_out, unsigned long long* hbig_clear, const unsigned long long* cum,
-                                        long long* log_row, const TableArgs ta) {
+__global__ void abm_hazard_table_kernel(const DevTables T, const unsigned long long* acc, unsigned long long* acc_next,
+                                        uint32_t* thr_out, unsigned long long* hbig_clear, unsigned long long* tally,
+                                        long long* counters, long long* log_row, const TableArgs ta) {
     const int n = T.P * T.A;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -672,41 +705,42 @@ __global__ void abm_hazard_table_kernel(const DevTables T, unsigned long long* a
         }
         thr_out[i] = thr;
     }
+    if (i < 2 * n) acc_next[i] = 0ull;
     if (i < T.n_big) hbig_clear[i] = 0ull;
-    if (blockIdx.x == 0 && ta.write_log && threadIdx.x < 8) {
+    if (blockIdx.x == 0 && threadIdx.x < 12) {
         const int t = threadIdx.x;
-        // cumulative date counters (base_model.py:1089-1090, 1097-1103)
-        if (t < 6) log_row[t] = (long long)cum[t] + (t == CUM_INFECTED ? ta.seeds_before_now : 0);
-        if (t == 6) log_row[ABM_C_ASYMPTOMATIC_COUNT] = (long long)cum[CUM_ASYM];
-        if (t == 7) { log_row[ABM_C_SYMPTOMATIC_COUNT] = (long long)cum[CUM_SYM]; log_row[ABM_C_TICK] = ta.tick; }
+        // counters[0..7] cumulative, counters[8..11] current exposed / contagious / hospitalised / critical
+        long long v = counters[t];
+        if (t < 8) {
+            v += (long long)tally[t];
+            tally[t] = 0ull;
+            counters[t] = v;
+            if (ta.write_log) {
+                const int col = t < 6 ? t : (t == 6 ? ABM_C_ASYMPTOMATIC_COUNT : ABM_C_SYMPTOMATIC_COUNT);
+                log_row[col] = v + (t == CUM_INFECTED ? ta.seeds_before_now : 0);
+            }
+        } else {
+            v += (long long)tally[PRE_EXPOSED + (t - 8)];
+            if (ta.write_log) log_row[ABM_C_CURRENT_EXPOSED_CASES + (t - 8)] = v;
+            v += (long long)tally[POST_EXPOSED + (t - 8)];
+            tally[PRE_EXPOSED + (t - 8)] = 0ull;
+            tally[POST_EXPOSED + (t - 8)] = 0ull;
+            counters[t] = v;
+        }
+        if (t == 0 && ta.write_log) log_row[ABM_C_TICK] = ta.tick;
     }
 }
 
-// second pass of the table kernel: snapshot + clear (separate launch so every thread of the first
-// pass has read the full row of R before it is zeroed)
-__global__ void abm_clear_tables_kernel(unsigned long long* acc, unsigned long long* acc_snapshot, int n2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n2) { acc_snapshot[i] = acc[i]; acc[i] = 0ull; }
-}
-
 // ------------------------------------------------------------------------------------------------ seeding
-__global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned long long* cum, const int64_t* slots,
+__global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned long long* tally, const int64_t* slots,
                                 const int64_t* ids, int64_t n, int32_t k, int32_t now) {
-    __shared__ unsigned int s_tally[N_TALLY];
-    if (threadIdx.x < N_TALLY) s_tally[threadIdx.x] = 0;
-    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const int64_t slot = slots[i];
         uint32_t a = G.aux[slot];
-        const uint32_t f = infect_agent(T, G, G.flags[slot], a, slot, ids[i], k, now, (uint32_t)k, s_tally);
+        const uint32_t f = infect_agent(T, G, G.flags[slot], a, slot, ids[i], k, now, (uint32_t)k, tally);
         G.flags[slot] = f;
         G.aux[slot] = a;
-    }
-    __syncthreads();
-    if (threadIdx.x == CUM_ASYM || threadIdx.x == CUM_SYM) {
-        const unsigned int v = s_tally[threadIdx.x];
-        if (v) atomicAdd(cum + threadIdx.x, (unsigned long long)v);
     }
 }
 
@@ -718,15 +752,14 @@ __global__ void abm_district_sym_kernel(const DevTables T, const DevAgents G, in
     if (slot >= n_slots) return;
     const uint32_t f = G.flags[slot];
     if (f & F_FILLER) return;
-    const int64_t tile = slot / ABM_TILE;
-    const int64_t cid = __ldg(T.tile_base + tile) + (slot - tile * ABM_TILE);
-    const uint32_t d = home_district(T, f, G.aux[slot], cid);
+    const uint32_t d = (uint32_t)(__ldg(T.sub_info + slot / SUB) >> 48);
     atomicAdd(pop + d, 1ull);
     const uint32_t epi = f & F_EPI_MASK;
     if ((epi == EPI_I || epi == EPI_C) && ((f >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) atomicAdd(sym + d, 1ull);
 }
 
-// current-state counters over all slots (abm_counters)
+// current-state counters over all slots (abm_counters): an independent recount of what the running
+// counters of the table kernel hold
 __global__ void abm_count_state_kernel(const DevAgents G, int64_t n_slots, unsigned long long* out4) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t c = 0;

@@ -22,7 +22,9 @@
 extern "C" {
 #endif
 
-#define ABM_TILE 1024            /* agent slots per tile (one thread block)                       */
+#define ABM_TILE 1024            /* agent slots per tile (one thread block of 8 warps)            */
+#define ABM_SUBTILE 128          /* agent slots per sub-tile (one warp): whole households of one   */
+                                 /* home district; slot offset o holds canonical id base + o       */
 #define ABM_BIG_HOUSEHOLD 32     /* households above this size use the global-atomic path         */
 #define ABM_MAX_STATUS 12        /* economic statuses                                             */
 #define ABM_QN 4096              /* bins of the quantile tables                                    */
@@ -97,9 +99,8 @@ typedef struct {
     const double*   p_hfat;       /* [128] AGE_HOSPITALIZATION_FATALITY_PROBABILITY           params.py:225 */
     const double*   severe_risk;  /* [D]   severe_disease_risk (ones under quirk Q2)          base_model.py:559 */
     const uint32_t* move_thr;     /* [n_move_classes][4] mover thresholds                     base_model.py:316-318 */
-    const int64_t*  district_start;/* [D+1] canonical id of the first agent of each home district       */
-    const int64_t*  tile_base;    /* [n_tiles+1] canonical id of the first agent of each tile           */
-    const uint16_t* tile_home;    /* [n_tiles] home district of the first agent of each tile            */
+    const uint64_t* sub_info;     /* [n_tiles * 8] per sub-tile: canonical id of slot 0 (multiple of 4) */
+                                  /*   in bits 0..47, home district of its agents in bits 48..63        */
     const int64_t*  big_start;    /* [n_big_households+1] canonical id of first member (+ sentinel)     */
 } abm_tables;
 

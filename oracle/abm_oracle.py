@@ -16,8 +16,8 @@ operating on reference-style vectors (epidemic_state, clinical_state, current_lo
 with three deliberate, documented differences (SURVEY.md sections 0, 8(c), A.4):
   1. time is an int32 minute tick since simulation start instead of a datetime object; `datetime.max`
      is T_NEVER.  Every reference comparison is `date < now`, kept strict.
-  2. every np.random call site is replaced by a lane of a counter-based Philox4x32-10 block keyed
-     (seed, step, agent, site) (oracle/philox.py); dwell times come from host-built quantile tables,
+  2. every np.random call site is replaced by a word of a counter-based Philox4x32-10 block keyed
+     (seed; agent or agent-group, step, site) (oracle/philox.py); dwell times come from host-built quantile tables,
      the length of stay from a Wilson-Hilferty transform of a table-based normal quantile.
   3. the explicit contact sampling of base_model.py:76-175 is restated in its mean-field
      "pressure table" form: an outside location L infects a susceptible of status b with probability
@@ -215,7 +215,8 @@ class OracleModel:
 
     # ------------------------------------------------------------------ base_model.py:304-441
     def go_out(self, now):
-        x0, x1, x2, x3 = philox.agent_draws(self.seed, self.k, self.agent_ids, philox.SITE_STEP)
+        x1 = philox.group_draws(self.seed, self.k, self.agent_ids, philox.SITE_MOVER)
+        x2 = philox.group_draws(self.seed, self.k, self.agent_ids, philox.SITE_OD)
         active = self.get_active(now)
         if self.weekday() <= 4:
             econ_move_prob = self.economic_status_weekday_movement_probability
@@ -238,7 +239,7 @@ class OracleModel:
         leaving, dst = cand[other], target[other]
         src = self.district_ids[leaving]
         par = self.tab['stay_par'][self.weekday(), src, dst]                                       # :418-428 (Q7)
-        xs = x3[leaving]
+        xs = philox.group_draws(self.seed, self.k, self.agent_ids[leaving], philox.SITE_STAY)
         mag = sample_quantile(self.tab['znorm'], (xs.astype(np.uint64) << np.uint64(1)) & np.uint64(0xFFFFFFFF))
         z = np.where(xs >> np.uint32(31) == 1, -mag, mag).astype(np.float64) * (1.0 / 65536.0)
         t = par[:, 1] + par[:, 2] * z
@@ -315,7 +316,7 @@ class OracleModel:
         exposed = hs > 0
         thr[h[exposed]] = hazard_threshold(hs[exposed].astype(np.float64) * (1.0 / TWO32))
         cand = np.nonzero(thr > 0)[0]
-        x0 = philox.agent_draws(self.seed, self.k, self.agent_ids[cand], philox.SITE_STEP)[0]
+        x0 = philox.group_draws(self.seed, self.k, self.agent_ids[cand], philox.SITE_INFECT)
         newly = cand[(x0 >> np.uint32(1)) < thr[cand]]
         self.set_epidemic_status(newly, now)
         return newly

@@ -3,10 +3,13 @@
 The CUDA kernels draw every random number from Philox4x32-10 (Salmon et al., SC'11,
 "Parallel random numbers: as easy as 1, 2, 3") with
     key     = (seed_lo, seed_hi)
-    counter = (agent_lo, agent_hi, step, site)
-This module restates the same generator with numpy uint64 arithmetic so the oracle step
-consumes bit-identical draws (every reference np.random call site
-becomes one lane of one of these blocks).
+    counter = (id_lo, id_hi, step, site)
+where id = agent id for the disease-course sites (one block per agent: `agent_draws`) and
+id = agent id >> 2 for the per-sub-step sites (one block per four consecutive agents, word
+agent id & 3 belongs to the agent: `group_draws`), so a GPU lane that owns four agents
+computes one block for all of them.  This module restates the same generator with numpy uint64
+arithmetic so the oracle step consumes bit-identical draws (every
+reference np.random call site becomes one word of one of these blocks).
 
 Known-answer vectors from the Random123 distribution (kat_vectors, philox4x32 10 rounds)
 are checked in tests/test_philox.py.
@@ -20,10 +23,13 @@ W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 SH32 = np.uint64(32)
 
-# Draw sites (the `site` word of the counter).  Lane meaning per site:
-SITE_STEP = 0      # x0 infection draw, x1 mover draw, x2 OD destination, x3 length-of-stay normal
-SITE_COURSE_A = 1  # x0 symptomatic?, x1 incubation / exposed->contagious dwell, x2 hospital?, x3 critical?
-SITE_COURSE_B = 2  # x0 critical fatality, x1 hospital fatality, x2 recovery dwell, x3 spare
+# Draw sites (the `site` word of the counter).
+SITE_INFECT = 0    # group block: infection draw of the sub-step            (base_model.py:143, 167)
+SITE_COURSE_A = 1  # agent block: x0 symptomatic?, x1 incubation / exposed->contagious dwell, x2 hospital?, x3 critical?
+SITE_COURSE_B = 2  # agent block: x0 critical fatality, x1 hospital fatality, x2 recovery dwell, x3 spare
+SITE_MOVER = 3     # group block: go_out mover draw                         (base_model.py:317)
+SITE_OD = 4        # group block: OD destination draw                       (base_model.py:374)
+SITE_STAY = 5      # group block: length-of-stay normal                     (base_model.py:431)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -59,3 +65,11 @@ def agent_draws(seed, step, agent_ids, site):
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return philox4x32_10(a & MASK, a >> SH32, np.uint64(int(step) & 0xFFFFFFFF), np.uint64(site),
                          seed & 0xFFFFFFFF, seed >> 32)
+
+
+def group_draws(seed, step, agent_ids, site):
+    """One uint32 per agent: word (agent & 3) of the block of group (agent >> 2) at (seed, step, site)."""
+    a = np.asarray(agent_ids).astype(np.uint64)
+    x = agent_draws(seed, step, a >> np.uint64(2), site)
+    w = (a & np.uint64(3)).astype(np.int64)
+    return np.choose(w, x) if a.ndim else x[int(w)]

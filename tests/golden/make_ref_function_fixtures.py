@@ -76,11 +76,17 @@ class DrawProvider:
     def _lanes(self, ids, site):
         return philox.agent_draws(self.o.seed, self.o.k, self.o.agent_ids[ids], site)
 
+    def _group(self, ids, site):
+        return philox.group_draws(self.o.seed, self.o.k, self.o.agent_ids[ids], site)
+
     def random(self, size=None):
         name, ids, _ = self._site()
         n = int(np.prod(size))
         assert n == ids.shape[0], (name, n, ids.shape)
-        lane = {'mover': (philox.SITE_STEP, 1), 'od': (philox.SITE_STEP, 2), 'sym': (philox.SITE_COURSE_A, 0),
+        if name in ('mover', 'od'):
+            u = u31(self._group(ids, philox.SITE_MOVER if name == 'mover' else philox.SITE_OD))
+            return u.reshape(size) if size is not None else u
+        lane = {'sym': (philox.SITE_COURSE_A, 0),
                 'hosp': (philox.SITE_COURSE_A, 2), 'crit': (philox.SITE_COURSE_A, 3),
                 'crit_fatal': (philox.SITE_COURSE_B, 0), 'hosp_fatal': (philox.SITE_COURSE_B, 1)}[name]
         u = u31(self._lanes(ids, lane[0])[lane[1]])
@@ -95,7 +101,7 @@ class DrawProvider:
             src = self.model.district_ids[ids]
             dst = np.asarray(f.f_locals['dst_district_ids'], dtype=np.int64)
             par = tab['stay_par'][dow, src, dst]
-            x3 = self._lanes(ids, philox.SITE_STEP)[3]
+            x3 = self._group(ids, philox.SITE_STAY)
             mag = sample_quantile(tab['znorm'], (x3.astype(np.uint64) << np.uint64(1)) & np.uint64(0xFFFFFFFF))
             z = np.where(x3 >> np.uint32(31) == 1, -mag, mag).astype(np.float64) / 65536.0
             t = par[:, 1] + par[:, 2] * z

@@ -3,34 +3,59 @@ import numpy as np
 from abm_b200 import constants as C, layout, synth
 
 
-def test_slot_map_keeps_households_inside_tiles():
+def test_slot_map_invariants():
+    """Sub-tiles hold whole small households of one home district; slot offset o <-> id base + o, base % 4 == 0."""
     spec = synth.make_spec(n_districts=5, seed=1)
     pop = synth.make_population(40_000, spec, seed=1)
     hh = pop.household.copy()
     hh[5000:5700] = hh[5000]                      # one camp-sized household
     _, hh = np.unique(hh, return_inverse=True)
-    sm = layout.build_slot_map(hh.astype(np.int64), agent_id_base=1_000_000)
-    assert sm.n_slots % C.TILE == 0 and sm.n_slots >= pop.n
-    assert sm.n_slots - pop.n < C.TILE + 0.01 * pop.n
-    assert np.array_equal(np.sort(sm.slot_of), sm.slot_of)           # canonical order preserved
-    tile = sm.slot_of // C.TILE
+    hh = hh.astype(np.int64)
+    base = 1_000_003                              # odd id base: leading fillers are needed
+    sm = layout.build_slot_map(hh, pop.district, agent_id_base=base)
+    S = C.SUBTILE
+    assert sm.n_slots % C.TILE == 0 and sm.n_slots >= pop.n and sm.n_subtiles * S == sm.n_slots
+    assert sm.n_slots - pop.n < C.TILE + 0.05 * pop.n
+    assert np.all(np.diff(sm.slot_of) > 0)                             # canonical order preserved
+    sub = sm.slot_of // S
     sizes = np.bincount(hh)
     small = sizes[hh] <= C.BIG_HOUSEHOLD
     first = np.r_[True, hh[1:] != hh[:-1]]
-    start_tile = tile[first][hh]                                       # tile of each agent's household head
-    assert np.all(tile[small] == start_tile[small])
-    assert sm.big_size.tolist() == [sizes.max()] and sm.big_start[0] == 1_000_000 + np.argmax(first & (sizes[hh] > 32))
-    # tile_base is the canonical id of the first agent in each tile; fillers only at tile ends
-    for t in range(sm.n_tiles):
-        cnt = sm.tile_base[t + 1] - sm.tile_base[t]
-        a = sm.agent_of[t * C.TILE:(t + 1) * C.TILE]
-        assert np.array_equal(a[:cnt], np.arange(cnt) + sm.tile_base[t] - 1_000_000) and np.all(a[cnt:] == -1)
+    start_sub = sub[first][hh]                                         # sub-tile of each agent's household head
+    assert np.all(sub[small] == start_sub[small])                      # small households do not straddle
+    for u in np.unique(sub):                                           # one home district per sub-tile
+        d = pop.district[sub == u]
+        assert d.min() == d.max() == sm.sub_home[u]
+    info = sm.sub_info
+    sub_base = (info & np.uint64((1 << 48) - 1)).astype(np.int64)
+    assert np.all(sub_base % 4 == 0)
+    assert np.array_equal((info >> np.uint64(48)).astype(np.int64), sm.sub_home)
+    ids = np.arange(pop.n) + base
+    assert np.array_equal(sub_base[sub] + sm.slot_of % S, ids)         # slot offset o holds id base + o
+    assert sm.big_size.tolist() == [sizes.max()] and sm.big_start[0] == base + np.argmax(first & (sizes[hh] > 32))
+    a = sm.agent_of
+    assert np.array_equal(a[sm.slot_of], np.arange(pop.n)) and (a >= 0).sum() == pop.n
+
+
+def test_slot_map_is_shard_invariant():
+    """A household-aligned shard gets the same sub-tile bases as the same agents in the whole population
+    when cut at a district boundary (ids, hence Philox groups, do not depend on the number of ranks)."""
+    spec = synth.make_spec(n_districts=4, seed=3)
+    pop = synth.make_population(20_000, spec, seed=3)
+    cut = int(np.searchsorted(pop.district, 2))
+    whole = layout.build_slot_map(pop.household, pop.district)
+    part = layout.build_slot_map(pop.household[cut:] - pop.household[cut], pop.district[cut:], agent_id_base=cut)
+    mask = (1 << 48) - 1
+    wb = (whole.sub_info & np.uint64(mask)).astype(np.int64)
+    pb = (part.sub_info & np.uint64(mask)).astype(np.int64)
+    used = np.unique(part.slot_of // C.SUBTILE)
+    assert set(pb[used]).issubset(set(wb))
 
 
 def test_pack_unpack_roundtrip_initial_state():
     spec = synth.make_spec(n_districts=4, seed=2)
     pop = synth.make_population(5_000, spec, seed=2)
-    sm = layout.build_slot_map(pop.household)
+    sm = layout.build_slot_map(pop.household, pop.district)
     flags, aux = layout.pack_flags(pop, sm)
     never = np.full(sm.n_slots, C.T_NEVER, np.int32)
     dev = dict(flags=flags, aux=aux, t_infected=never, t_contagious=never, t_onset=never, t_recovered=never,
