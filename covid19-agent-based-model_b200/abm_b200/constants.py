@@ -24,32 +24,37 @@ T_NEVER = np.int32(2**31 - 1)  # datetime.max in the reference
 FIRE_NEVER = 0xFFFF            # "no pending event" in the 16-bit next-event field
 
 # ----------------------------------------------------------------------------- hot-record bit layout
-# flags word (uint32) -- one per agent slot, read every sub-step.
+# flags word (uint32) -- one per agent slot, read every sub-step.  Fields the kernel tests together sit
+# next to each other (state + location in the low byte; byte 2 is the index into the rate tables).
 F_EPI_SHIFT, F_EPI_MASK = 0, 0x7          # epidemic state 0..4
 F_CLIN_SHIFT, F_CLIN_MASK = 3, 0x3        # clinical state 0..3
-F_SYM_SHIFT, F_SYM_MASK = 5, 0x3          # 0 none, 1 asymptomatic, 2 symptomatic
-F_LOC_SHIFT, F_LOC_MASK = 7, 0x7          # location kind (LOC_*)
-F_AWAY = 1 << 10                          # return_district_at != max
-F_DMOVER = 1 << 11                        # district_mover
+F_LOC_SHIFT, F_LOC_MASK = 5, 0x7          # location kind (LOC_*)
+F_AWAY = 1 << 8                           # return_district_at != max
+F_DMOVER = 1 << 9                         # district_mover
+F_HEAD = 1 << 10                          # first member of its household (segment head)
+F_ONSET = 1 << 11                         # symptom onset has passed (date_start_symptomatic < now)
 F_STATUS_SHIFT, F_STATUS_MASK = 12, 0xF   # economic status id
 F_AGE_SHIFT, F_AGE_MASK = 16, 0x7F        # age 0..99
-F_HEAD = 1 << 23                          # first member of its household (segment head)
-F_OUT_H = 1 << 24                         # will be hospitalised
-F_OUT_C = 1 << 25                         # will need critical care
-F_OUT_D = 1 << 26                         # will die
-F_ONSET = 1 << 27                         # symptom onset has passed (date_start_symptomatic < now)
+F_SYMPT = 1 << 23                         # infected_symptomatic_status == SYMPTOMATIC  (age | F_SYMPT = rate index)
+F_ASYMPT = 1 << 24                        # infected_symptomatic_status == ASYMPTOMATIC
+F_OUT_H = 1 << 25                         # will be hospitalised
+F_OUT_C = 1 << 26                         # will need critical care
+F_OUT_D = 1 << 27                         # will die
 F_EKIND_SHIFT, F_EKIND_MASK = 28, 0x3     # economic-activity location kind (EKIND_*)
 F_BIGHH = 1 << 30                         # member of a household larger than BIG_HOUSEHOLD
 F_FILLER = 1 << 31                        # padding slot, not a person
+# aux word (uint32): high 16 = sub-step index at which the next scheduled event fires (FIRE_NEVER = none),
+#                    low 16  = current district id
+AUX_FIRE_SHIFT = 16
 
 # location kinds say WHERE the agent is (the reference's location id follows from it):
 #   HOME      own household                                   -> household id
-#   CUR       outside pool of its current district            -> current_district id (economic activity in the
-#             home district, or the destination district of a trip; base_model.py:337-339, 436-439)
-#   HOMEPOOL  outside pool of the HOME district while away    -> home district id (quirk Q4)
+#   HOMEPOOL  outside pool of its HOME district               -> home district id (economic activity there,
+#             also for travellers that are away on paper: quirk Q4; base_model.py:331-339)
+#   DEST      outside pool of the destination of a trip       -> current_district id (base_model.py:436-439)
 #   POOL      extra outside location (school)                 -> its economic_activity_location id
 #   HOSP      hospital = -current_district (base_model.py:270-272);  DEAD = -1
-LOC_HOME, LOC_CUR, LOC_HOMEPOOL, LOC_POOL, LOC_HOSP, LOC_DEAD = 0, 1, 2, 3, 4, 5
+LOC_HOME, LOC_HOMEPOOL, LOC_DEST, LOC_POOL, LOC_HOSP, LOC_DEAD = 0, 1, 2, 3, 4, 5
 EKIND_HOUSEHOLD, EKIND_HOME_DISTRICT, EKIND_POOL = 0, 1, 2
 
 TILE = 1024           # agent slots per thread block (8 warps x SUBTILE)

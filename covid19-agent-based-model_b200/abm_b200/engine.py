@@ -40,13 +40,13 @@ class AbmConfig(ct.Structure):
 class AbmTables(ct.Structure):
     _fields_ = [(n, ct.c_void_p) for n in
                 ('rfx', 'qfx', 'W', 'pool_hw', 'od_thr', 'stay_par', 'dwell', 'znorm', 'p_hosp', 'p_crit', 'p_hfat',
-                 'severe_risk', 'move_thr', 'sub_info', 'big_start')]
+                 'severe_risk', 'move_thr', 'sub_info', 'big_start', 'omexp')]
 
 
 class AbmAgentPtrs(ct.Structure):
     _fields_ = [(n, ct.c_void_p) for n in
                 ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
-                 'move_class', 'econ_pool')]
+                 'move_class', 'econ_pool', 'hh_index')]
 
 
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
@@ -144,6 +144,7 @@ class Simulation:
             t_onset=dev(np.full(n_slots, never, np.int32)), t_recovered=dev(np.full(n_slots, never, np.int32)),
             t_return=dev(np.full(n_slots, never, np.int32)), inf_at=dev(np.zeros(n_slots, np.int32)),
             move_class=dev(slots_from_agents(self.move_class, 0, np.uint16).view(np.int16)),
+            hh_index=dev(layout.household_index(flags)),
         )
         if pop.econ_pool is not None:
             self.buf['econ_pool'] = dev(slots_from_agents(pop.econ_pool.astype(np.int32), 0, np.int32))
@@ -177,14 +178,14 @@ class Simulation:
             rfx=t['rfx'], qfx=t['qfx'], W=t['W'], pool_hw=t['pool_hw'], od_thr=t['od_thr'], stay_par=t['stay_par'],
             dwell=t['dwell'], znorm=t['znorm'], p_hosp=t['p_hosp'], p_crit=t['p_crit'], p_hfat=t['p_hfat'],
             severe_risk=t['severe_risk'], move_thr=self.move_thr, sub_info=np.ascontiguousarray(sm.sub_info),
-            big_start=np.ascontiguousarray(sm.big_start))
+            big_start=np.ascontiguousarray(sm.big_start), omexp=t['omexp'])
         at = AbmTables()
         for name, arr in keep.items():
             setattr(at, name, _ptr(arr))
         self._check(self.lib.abm_set_tables(self.h, ct.byref(at)))
         ap = AbmAgentPtrs()
         for name in ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
-                     'move_class'):
+                     'move_class', 'hh_index'):
             setattr(ap, name, self.buf[name].data_ptr())
         ap.econ_pool = self.buf['econ_pool'].data_ptr() if 'econ_pool' in self.buf else None
         self._check(self.lib.abm_bind_agents(self.h, ct.byref(ap)))

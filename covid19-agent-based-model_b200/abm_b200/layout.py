@@ -5,12 +5,14 @@ slots, one per thread block):
   hot, read every sub-step (8 B/agent):
     flags  uint32   bit fields of constants.F_*  (epidemic / clinical / symptomatic state, location kind,
                     away, district_mover, economic status, age, household-head bit, outcome bits, ...)
-    aux    uint32   low 16: sub-step index at which the next scheduled event fires (FIRE_NEVER = none)
-                    high 16: current district id
+    aux    uint32   high 16: sub-step index at which the next scheduled event fires (FIRE_NEVER = none)
+                    low 16: current district id
   cold, touched only when an event fires, on infection, or on the two movement sub-steps for travellers:
     t_infected, t_contagious, t_onset, t_recovered, t_return   int32 minute ticks
     inf_at uint32   (location kind << 16) | district at infection
     move_class uint16  index into the movement-probability threshold table (read at go_out only)
+    hh_index   uint8   index of the slot's household within its sub-tile (static; read by warps that hold
+                       a contagious agent at home)
     econ_pool  uint32  outside-pool row for EKIND_POOL agents (schools), allocated only when used
 Agents are in canonical order (home district, household).  A sub-tile holds whole households (of
 <= BIG_HOUSEHOLD members) of ONE home district, and slot offset o of a sub-tile holds canonical agent id
@@ -147,9 +149,19 @@ def pack_flags(pop: Population, sm: SlotMap):
                        | (C.CLINICAL_RELEASED_OR_DEAD << C.F_CLIN_SHIFT))
     flags = np.full(sm.n_slots, filler, dtype=np.uint32)
     flags[sm.slot_of] = f
-    aux = np.full(sm.n_slots, C.FIRE_NEVER, dtype=np.uint32)
-    aux[sm.slot_of] = (pop.district.astype(np.uint32) << np.uint32(16)) | np.uint32(C.FIRE_NEVER)
+    never = np.uint32(C.FIRE_NEVER << C.AUX_FIRE_SHIFT)
+    aux = np.full(sm.n_slots, never, dtype=np.uint32)
+    aux[sm.slot_of] = pop.district.astype(np.uint32) | never
     return flags, aux
+
+
+def household_index(flags: np.ndarray):
+    """uint8 [n_slots]: number of household heads (fillers count as heads) up to each slot within its
+    sub-tile, minus one.  255 for members of a big household that continue at the start of a sub-tile
+    (they never use it)."""
+    head = ((flags & np.uint32(C.F_HEAD)) != 0).reshape(-1, C.SUBTILE)
+    idx = np.cumsum(head, axis=1, dtype=np.int32) - 1
+    return (idx & 0xFF).astype(np.uint8).reshape(-1)
 
 
 def update_static_fields(flags: np.ndarray, pop: Population, sm: SlotMap):
@@ -172,9 +184,9 @@ def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_ho
     D = n_districts
     epi = ((f >> C.F_EPI_SHIFT) & C.F_EPI_MASK).astype(np.int8)
     clin = ((f >> C.F_CLIN_SHIFT) & C.F_CLIN_MASK).astype(np.int8)
-    symc = ((f >> C.F_SYM_SHIFT) & C.F_SYM_MASK).astype(np.int8)
+    sym_status = np.where((f & C.F_SYMPT) != 0, 1, np.where((f & C.F_ASYMPT) != 0, 0, -1)).astype(np.int8)
     kind = ((f >> C.F_LOC_SHIFT) & C.F_LOC_MASK).astype(np.int64)
-    cur = (aux >> 16).astype(np.int64)
+    cur = (aux & 0xFFFF).astype(np.int64)
     household_ids = pop.household.astype(np.int64) + D
     H = pop.n_households
     econ_loc = np.where(pop.econ_kind == C.EKIND_HOUSEHOLD, household_ids, pop.district.astype(np.int64))
@@ -182,9 +194,9 @@ def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_ho
         econ_loc = np.where(pop.econ_kind == C.EKIND_POOL, D + H + (pop.econ_pool.astype(np.int64) - D), econ_loc)
 
     def loc_from(kind, cur):
-        return np.select([kind == C.LOC_HOME, kind == C.LOC_CUR, kind == C.LOC_HOMEPOOL, kind == C.LOC_POOL,
+        return np.select([kind == C.LOC_HOME, kind == C.LOC_HOMEPOOL, kind == C.LOC_DEST, kind == C.LOC_POOL,
                           kind == C.LOC_HOSP],
-                         [household_ids, cur, pop.district.astype(np.int64), econ_loc, -cur], default=-1)
+                         [household_ids, pop.district.astype(np.int64), cur, econ_loc, -cur], default=-1)
 
     away = (f & C.F_AWAY) != 0
     infected = dev['t_infected'][s] != T_NEVER
@@ -195,7 +207,7 @@ def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_ho
     never = np.int64(T_NEVER)
     inf_at = dev['inf_at'][s]
     out = dict(
-        epidemic_state=epi, clinical_state=clin, infected_symptomatic_status=(symc - 1).astype(np.int8),
+        epidemic_state=epi, clinical_state=clin, infected_symptomatic_status=sym_status,
         current_location_ids=loc_from(kind, cur), current_district_ids=cur,
         return_district_at=np.where(away, dev['t_return'][s], T_NEVER).astype(np.int32),
         date_infected=dev['t_infected'][s].astype(np.int32),

@@ -5,12 +5,15 @@ is tabulated here once, on the host, as integers:
   * dwell-time quantile tables (minutes) for the four sampled periods of `set_epidemic_status`
     (base_model.py:868-874, 1011-1017, 1036-1050; distributions params.py:145-189),
   * half-normal quantile table (fixed point 2^-16) for the length-of-stay transform,
-  * fixed-point infection rates (2^-32) per age and symptomatic status (params.py:236-242) and the
+  * fixed-point infection rates (2^-24) per age and symptomatic status (params.py:236-242) and the
     matching household log-survival increments -log(1 - 3 r) (base_model.py:184-187),
+  * the hazard -> infection-probability table 1 - exp(-i/256) in 0.32 fixed point (the remainder of the
+    hazard goes through an integer Taylor polynomial, see oracle.hazard_threshold_fx),
   * 31-bit Bernoulli thresholds ceil(p * 2^31) for mover draws and OD destination rows
     (base_model.py:316-318, 372-377).
-What remains in floating point on the device is a fixed sequence of IEEE-754 double +, *, / evaluated
-without FMA contraction, mirrored op for op by the oracle.
+What remains in floating point on the device (the district x status hazard and the length-of-stay
+transform) is a fixed sequence of IEEE-754 double +, *, / evaluated without FMA contraction, mirrored op
+for op by the oracle.
 """
 import numpy as np
 from scipy import stats
@@ -22,6 +25,8 @@ QBITS = 12
 QN = 1 << QBITS                 # 4096 bins in the main table and in the tail table
 TWO31 = 2147483648.0
 TWO32 = 4294967296.0
+RATE_SCALE = 16777216.0         # 2^24: fixed-point unit of the rate / log-survival tables
+OMEXP_N = 8192                  # entries of the 1 - exp(-i/256) table: hazards up to 32
 DWELL_INCUBATION, DWELL_ASYM_TO_CONTAGIOUS, DWELL_SYM_RECOVERY, DWELL_ASYM_RECOVERY = 0, 1, 2, 3
 
 
@@ -54,6 +59,12 @@ def znorm_table():
     return np.ascontiguousarray(np.rint(knots * 65536.0).astype(np.int32))
 
 
+def omexp_table():
+    """uint32 [OMEXP_N]: round((1 - exp(-i / 256)) * 2^32)."""
+    i = np.arange(OMEXP_N, dtype=np.float64)
+    return np.minimum(np.rint(-np.expm1(-i / 256.0) * TWO32), TWO32 - 1).astype(np.uint32)
+
+
 def bern_threshold(p):
     """T with  (x >> 1) < T  <=>  (x >> 1) / 2^31 < p  for every 32-bit x."""
     p = np.clip(np.asarray(p, dtype=np.float64), 0.0, 1.0)
@@ -84,13 +95,15 @@ def build_tables(spec: ModelSpec):
     at = spec.age_tables()
     pad = lambda v: np.concatenate([v, np.repeat(v[-1], 128 - v.shape[0])])
     r = np.stack([pad(at['r_asym']), pad(at['r_sym'])])                      # [2, 128]
-    rfx = np.rint(r * TWO32).astype(np.uint32)
+    rfx = np.rint(r * RATE_SCALE).astype(np.uint32)
     hw = np.ones(1) if spec.hw_risk is None else np.asarray(spec.hw_risk, dtype=np.float64)
     hr = C.HOUSEHOLD_RATE_FACTOR * r[None, :, :] * hw[:, None, None]         # [hw_rows, 2, 128]
     if np.any(hr >= 1.0):
         raise ValueError('household infection probability >= 1')
-    qfx = np.rint(-np.log1p(-hr) * TWO32).astype(np.uint32)
-    W = (spec.interaction_sizes[:, None] * spec.interaction_matrix) * (1.0 / TWO32)   # [A(infector), A(contact)]
+    qfx = np.rint(-np.log1p(-hr) * RATE_SCALE).astype(np.uint32)
+    if qfx.max() * C.BIG_HOUSEHOLD >= 2 ** 32:
+        raise ValueError('household hazard sum would overflow 32 bits')
+    W = (spec.interaction_sizes[:, None] * spec.interaction_matrix) * (1.0 / RATE_SCALE)   # [A(infector), A(contact)]
     pool_district = np.concatenate([np.arange(D, dtype=np.int32),
                                     np.asarray(spec.extra_pool_district, dtype=np.int32)])
     pool_hw = np.ones(P) if spec.hw_risk is None else hw[pool_district]
@@ -105,7 +118,7 @@ def build_tables(spec: ModelSpec):
         W=np.ascontiguousarray(W), pool_hw=np.ascontiguousarray(pool_hw, dtype=np.float64),
         pool_district=pool_district,
         od_thr=np.ascontiguousarray(od_thr), stay_par=np.ascontiguousarray(stay_par),
-        dwell=dwell_tables(), znorm=znorm_table(),
+        dwell=dwell_tables(), znorm=znorm_table(), omexp=omexp_table(),
         p_hosp=np.ascontiguousarray(pad(at['p_hosp'])), p_crit=np.ascontiguousarray(pad(at['p_crit'])),
         p_hfat=np.ascontiguousarray(pad(at['p_hfat'])),
         severe_risk=np.ascontiguousarray(spec.severe_risk, dtype=np.float64),

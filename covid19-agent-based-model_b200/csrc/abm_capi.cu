@@ -37,7 +37,9 @@ struct abm_handle {
     DevAgents G{};
     bool have_tables = false, have_agents = false;
     std::vector<void*> owned;           // device allocations to free
-    unsigned long long* acc[2] = {nullptr, nullptr};   // [2][P][A] each; sub-step k accumulates into acc[k & 1]
+    unsigned long long* acc[2] = {nullptr, nullptr};   // [replicas][2][P][A] each; sub-step k accumulates into acc[k & 1]
+    unsigned long long* acc_sum = nullptr;             // [2][P][A] replicas (and ranks) summed: tables of the last sub-step
+    int32_t replicas = 1;
     uint32_t* thr_out = nullptr;        // [P][A]
     unsigned long long* hbig[2] = {nullptr, nullptr};
     unsigned long long* tally = nullptr;   // [N_TALLY] per-launch event tallies, folded by the table kernel
@@ -117,6 +119,7 @@ int launch_main(abm_handle* h, const StepArgs& s) {
     w.hbig_write = h->hbig[s.k & 1];
     w.hbig_read = h->hbig[(s.k + 1) & 1];
     w.tally = h->tally;
+    w.rep_mask = (uint32_t)h->replicas - 1u;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->prof_used == h->prof_events.size()) {
@@ -134,9 +137,9 @@ int launch_main(abm_handle* h, const StepArgs& s) {
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
 #define ABM_LAUNCH(MODE) abm_substep_kernel<MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s)
     if (m == (M_INFECT | M_STEP)) ABM_LAUNCH(M_INFECT | M_STEP);                                        // night
-    else if (m == (M_INFECT | M_STEP | M_DENSE)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE);               // day
-    else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE);
-    else if (m == (M_INFECT | M_STEP | M_GO_HOME)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_HOME);
+    else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A);   // day
+    else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
+    else if (m == (M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I);
     else if (m == M_INFECT) ABM_LAUNCH(M_INFECT);                                                       // abm_flush
     else ABM_LAUNCH(RUNTIME_MODE);
 #undef ABM_LAUNCH
@@ -188,6 +191,7 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     *out = h;   // returned even on failure so the caller can read the message, then abm_destroy
     h->cfg = *cfg;
     if (cfg->n_slots <= 0 || cfg->n_slots != cfg->n_tiles * ABM_TILE) return fail(h, ABM_ERR_ARG, "n_slots must be n_tiles * %d", ABM_TILE);
+    if (cfg->n_slots >= (1ll << 31)) return fail(h, ABM_ERR_ARG, "at most 2^31 - 1 agent slots per rank (shard the population)");
     if (cfg->n_status < 1 || cfg->n_status > ABM_MAX_STATUS) return fail(h, ABM_ERR_ARG, "n_status must be 1..%d", ABM_MAX_STATUS);
     if (cfg->n_districts < 1 || cfg->n_districts > 65535 || cfg->n_pools < cfg->n_districts) return fail(h, ABM_ERR_ARG, "bad district / pool count");
     if (cfg->hw_rows != 1 && cfg->hw_rows != cfg->n_districts) return fail(h, ABM_ERR_ARG, "hw_rows must be 1 or n_districts");
@@ -200,12 +204,16 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     h->stream = (cudaStream_t)cfg->stream;   // NULL is the legacy default stream, which is also torch's default
     const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
     int rc;
-    if ((rc = alloc_zero(h, 2 * pa, &h->acc[0]))) return rc;
-    if ((rc = alloc_zero(h, 2 * pa, &h->acc[1]))) return rc;
+    // replicas of the accumulators: a power of two <= 64 keeping each table buffer under 8 MiB
+    h->replicas = 64;
+    while (h->replicas > 1 && (size_t)h->replicas * 2 * pa * sizeof(unsigned long long) > (8u << 20)) h->replicas >>= 1;
+    if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[0]))) return rc;
+    if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[1]))) return rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc_sum))) return rc;
     if ((rc = alloc_zero(h, pa, &h->thr_out))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[0]))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[1]))) return rc;
-    if ((rc = alloc_zero(h, (size_t)N_TALLY, &h->tally))) return rc;
+    if ((rc = alloc_zero(h, (size_t)h->replicas * N_TALLY, &h->tally))) return rc;
     if ((rc = alloc_zero(h, (size_t)12, &h->counters))) return rc;
     if ((rc = alloc_zero(h, (size_t)(cfg->max_log_rows + 1) * ABM_LOG_STRIDE, &h->daylog))) return rc;
     if (cfg->world_size > 1) {
@@ -254,6 +262,7 @@ int abm_set_tables(abm_handle* h, const abm_tables* t) {
         T.sub_info = si;
     }
     if ((rc = upload(h, t->big_start, (size_t)c.n_big_households + 1, &T.big_start))) return rc;
+    if ((rc = upload(h, t->omexp, (size_t)ABM_OMEXP_N, &T.omexp))) return rc;
     T.D = c.n_districts; T.A = c.n_status; T.P = c.n_pools; T.hw_rows = c.hw_rows; T.n_big = c.n_big_households;
     T.step_ticks = c.step_ticks; T.mild_active = c.mild_active;
     T.step_inv = ~0ull / (unsigned long long)c.step_ticks + 1ull;   // floor(2^64 / step) + 1 for step >= 2 not a power of two; exact use in fire_index
@@ -270,13 +279,15 @@ int abm_set_tables(abm_handle* h, const abm_tables* t) {
 int abm_bind_agents(abm_handle* h, const abm_agent_ptrs* dev) {
     if (!h || !dev) return ABM_ERR_ARG;
     if (!dev->flags || !dev->aux || !dev->t_infected || !dev->t_contagious || !dev->t_onset || !dev->t_recovered ||
-        !dev->t_return || !dev->inf_at || !dev->move_class)
+        !dev->t_return || !dev->inf_at || !dev->move_class || !dev->hh_index)
         return fail(h, ABM_ERR_ARG, "null agent buffer");
     if (((uintptr_t)dev->flags | (uintptr_t)dev->aux) & 15) return fail(h, ABM_ERR_ARG, "flags/aux must be 16-byte aligned");
+    if (((uintptr_t)dev->move_class & 7) || ((uintptr_t)dev->hh_index & 3)) return fail(h, ABM_ERR_ARG, "move_class / hh_index misaligned");
     DevAgents& G = h->G;
     G.flags = dev->flags; G.aux = dev->aux; G.t_infected = dev->t_infected; G.t_contagious = dev->t_contagious;
     G.t_onset = dev->t_onset; G.t_recovered = dev->t_recovered; G.t_return = dev->t_return; G.inf_at = dev->inf_at;
     G.move_class = dev->move_class; G.econ_pool = dev->econ_pool;
+    G.hh_index = reinterpret_cast<const uint32_t*>(dev->hh_index);
     h->have_agents = true;
     return ABM_OK;
 }
@@ -330,9 +341,10 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
         StepArgs s{};
         s.k = (int32_t)h->k; s.now = (int32_t)tick; s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks; s.weekday = wd;
         s.mode = M_STEP | (h->pending_infect ? M_INFECT : 0u);
+        if (h->daytime && h->pending_infect) s.mode |= M_DENSE_I;     // the draw applied now belongs to a daytime sub-step
         if (hour == 8) { s.mode |= M_GO_OUT; h->daytime = true; }     // params.py:131,135
         if (hour == 16) { s.mode |= M_GO_HOME; h->daytime = false; }  // params.py:132,136
-        if (h->daytime) s.mode |= M_DENSE;
+        if (h->daytime) s.mode |= M_DENSE_A;
         if (wd <= 4) s.mode |= M_WEEKDAY;             // base_model.py:309
         const bool log = hour == 8;                   // base_model.py:1083
         long long* row = h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE;   // scratch row
@@ -343,22 +355,34 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
         }
         int rc = launch_main(h, s);
         if (rc) return rc;
-        unsigned long long* acc = h->acc[s.k & 1];
-        if (h->comm) {
-            ncclResult_t r = h->nccl_allreduce(acc, acc, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
-            if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
-        }
         TableArgs ta{};
+        ta.replicas = h->replicas;
         ta.write_log = log ? 1 : 0;
         ta.tick = (int32_t)tick;
         ta.seeds_before_now = 0;
         for (const SeedEvent& e : h->seeds)
             if (e.tick < tick) ta.seeds_before_now += e.n;
-        const int nthreads = 2 * pa > c.n_big_households ? 2 * pa : c.n_big_households;
-        abm_hazard_table_kernel<<<(nthreads + 127) / 128, 128, 0, h->stream>>>(h->T, acc, h->acc[(s.k + 1) & 1], h->thr_out,
-                                                                              h->hbig[(s.k + 1) & 1], h->tally, h->counters, row, ta);
+        unsigned long long* acc = h->acc[s.k & 1];
+        unsigned long long* acc_next = h->acc[(s.k + 1) & 1];
+        unsigned long long* hbig_next = h->hbig[(s.k + 1) & 1];
+        if (h->comm) {
+            // sum the replicas, sum over ranks, then derive the thresholds from the global tables
+            ta.do_reduce = 1; ta.do_threshold = 0;
+            abm_hazard_table_kernel<<<c.n_pools, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
+                                                                     h->tally, h->counters, row, ta);
+            ncclResult_t r = h->nccl_allreduce(h->acc_sum, h->acc_sum, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
+            if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
+            ta.do_reduce = 0; ta.do_threshold = 1;
+            abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
+                                                                         h->tally, h->counters, row, ta);
+            h->launches += 2;
+        } else {
+            ta.do_reduce = 1; ta.do_threshold = 1;
+            abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
+                                                                         h->tally, h->counters, row, ta);
+            h->launches += 1;
+        }
         CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
         if (log) h->n_log_rows++;
         h->k++;
         h->pending_infect = true;
@@ -373,7 +397,7 @@ int abm_flush(abm_handle* h) {
     StepArgs s{};
     s.k = (int32_t)h->k; s.now = (int32_t)(h->k * c.step_ticks); s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks;
     s.weekday = weekday_of(c, s.now);
-    s.mode = M_INFECT;
+    s.mode = M_INFECT | (h->daytime ? M_DENSE_I : 0u);
     int rc = launch_main(h, s);
     if (rc) return rc;
     h->pending_infect = false;
@@ -404,14 +428,18 @@ int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
     CUDA_TRY(h, cudaMemsetAsync(d4, 0, 4 * sizeof(unsigned long long), h->stream));
     const int64_t n = h->cfg.n_slots;
     abm_count_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->G, n, d4);
-    unsigned long long cur[4], pend[N_TALLY];
+    unsigned long long cur[4];
+    std::vector<unsigned long long> pend((size_t)h->replicas * N_TALLY);
     long long run[12], cum[8];
     CUDA_TRY(h, cudaMemcpyAsync(cur, d4, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(pend, h->tally, sizeof pend, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(pend.data(), h->tally, pend.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(run, h->counters, sizeof run, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d4);
-    for (int i = 0; i < 8; ++i) cum[i] = run[i] + (long long)pend[i];   // tallies of a flush are folded by the next table kernel
+    for (int i = 0; i < 8; ++i) {       // tallies of a flush are folded by the next table kernel
+        cum[i] = run[i];
+        for (int r = 0; r < h->replicas; ++r) cum[i] += (long long)pend[(size_t)r * N_TALLY + i];
+    }
     h->launches++;
     // NOTE: cumulative date counters cover events whose date precedes the LAST executed sub-step's clock;
     // the day log (abm_read_log) holds the exact log_model_output values.
@@ -456,7 +484,7 @@ int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* th
     if (!h) return ABM_ERR_ARG;
     const size_t pa = (size_t)h->cfg.n_pools * h->cfg.n_status;
     if (h->k < 1) return fail(h, ABM_ERR_STATE, "no sub-step executed yet");
-    const unsigned long long* last = h->acc[(h->k - 1) & 1];    // tables of the last executed sub-step
+    const unsigned long long* last = h->acc_sum;                // tables of the last executed sub-step
     if (rsum) CUDA_TRY(h, cudaMemcpyAsync(rsum, last, pa * 8, cudaMemcpyDeviceToHost, h->stream));
     if (ncnt) CUDA_TRY(h, cudaMemcpyAsync(ncnt, last + pa, pa * 8, cudaMemcpyDeviceToHost, h->stream));
     if (thr) CUDA_TRY(h, cudaMemcpyAsync(thr, h->thr_out, pa * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -18,10 +18,12 @@
 // households of a single home district and that slot offset o of a sub-tile is canonical agent id
 // base + o with base a multiple of 4, so (a) the household hazard is a warp-local segmented sum,
 // (b) the home district is a per-warp scalar and (c) one Philox4x32 block serves the four agents of a
-// lane.  Warps never wait for each other except for one block-wide flush of the per-CTA counters.
-// Work that only a few agents need (disease-course sampling, due transitions, travellers) runs in
-// "funnel" loops: every lane keeps a bit mask of its agents that need it and the warp iterates until
-// all masks are empty, so the cost is max-per-lane, not four passes.
+// lane.  Warps never wait for each other: per-CTA counters are flushed by whichever warp finishes last.
+// The kernel is instruction-issue bound, not HBM bound (profiles/), so the code below is organised to
+// issue few instructions: flag fields that are tested together are adjacent, work that only a few agents
+// need (disease-course sampling, due transitions, travellers) runs in "funnel" loops -- every lane keeps
+// a bit mask of its agents that need it and the warp iterates until all masks are empty, so the cost
+// is max-per-lane, not four passes -- and the hazard -> probability map is integer arithmetic.
 //
 // All random numbers are Philox4x32-10 keyed by the seed.  Counter = (id, id >> 32, sub-step, site):
 // id = agent_id >> 2 for the group sites (word agent_id & 3 belongs to the agent), id = agent_id for
@@ -37,27 +39,31 @@
 namespace abm {
 
 // ---- flags word (constants.py F_*)
-constexpr uint32_t F_EPI_MASK = 0x7u, F_CLIN_SHIFT = 3, F_CLIN_MASK = 0x3u, F_SYM_SHIFT = 5, F_SYM_MASK = 0x3u;
-constexpr uint32_t F_LOC_SHIFT = 7, F_LOC_MASK = 0x7u;
-constexpr uint32_t F_AWAY = 1u << 10, F_DMOVER = 1u << 11;
+constexpr uint32_t F_EPI_MASK = 0x7u, F_CLIN_SHIFT = 3, F_CLIN_MASK = 0x3u, F_LOC_SHIFT = 5, F_LOC_MASK = 0x7u;
+constexpr uint32_t F_AWAY = 1u << 8, F_DMOVER = 1u << 9, F_HEAD = 1u << 10, F_ONSET = 1u << 11;
 constexpr uint32_t F_STATUS_SHIFT = 12, F_STATUS_MASK = 0xFu, F_AGE_SHIFT = 16, F_AGE_MASK = 0x7Fu;
-constexpr uint32_t F_HEAD = 1u << 23, F_OUT_H = 1u << 24, F_OUT_C = 1u << 25, F_OUT_D = 1u << 26, F_ONSET = 1u << 27;
+constexpr uint32_t F_SYMPT = 1u << 23, F_ASYMPT = 1u << 24, F_OUT_H = 1u << 25, F_OUT_C = 1u << 26, F_OUT_D = 1u << 27;
 constexpr uint32_t F_EKIND_SHIFT = 28, F_EKIND_MASK = 0x3u, F_BIGHH = 1u << 30, F_FILLER = 1u << 31;
-// where the agent is: own household / outside pool of its current district / outside pool of its HOME
-// district while away (quirk Q4) / extra outside pool (school) / hospital (-current_district) / dead
-constexpr uint32_t LOC_HOME = 0, LOC_CUR = 1, LOC_HOMEPOOL = 2, LOC_POOL = 3, LOC_HOSP = 4, LOC_DEAD = 5;
+// where the agent is: own household / outside pool of its HOME district (also while away on paper,
+// quirk Q4) / outside pool of the destination of a trip / extra outside pool (school) / hospital
+// (-current_district) / dead
+constexpr uint32_t LOC_HOME = 0, LOC_HOMEPOOL = 1, LOC_DEST = 2, LOC_POOL = 3, LOC_HOSP = 4, LOC_DEAD = 5;
 constexpr uint32_t EKIND_HOUSEHOLD = 0, EKIND_HOME_DISTRICT = 1, EKIND_POOL = 2;
 constexpr uint32_t EPI_S = 0, EPI_I = 1, EPI_C = 2, EPI_R = 3, EPI_D = 4;
 constexpr int32_t T_NEVER = 0x7FFFFFFF;
 constexpr uint32_t FIRE_NEVER = 0xFFFFu;
 constexpr int32_t DAY = 1440;
 constexpr uint32_t LOCF = F_LOC_MASK << F_LOC_SHIFT;
+constexpr uint32_t CLINF = F_CLIN_MASK << F_CLIN_SHIFT;
+constexpr uint32_t IN_HOMEPOOL = LOC_HOMEPOOL << F_LOC_SHIFT;
 
 // ---- Philox sites (oracle/philox.py)
 constexpr uint32_t SITE_INFECT = 0, SITE_COURSE_A = 1, SITE_COURSE_B = 2, SITE_MOVER = 3, SITE_OD = 4, SITE_STAY = 5;
 
-// ---- step modes
-constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32, M_DENSE = 64;
+// ---- step modes.  DENSE_I / DENSE_A: most agents were / are in an outside pool (daytime) at the sub-step
+// whose infection draw is applied / whose tables are accumulated; any data is handled correctly either way
+constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32, M_DENSE_I = 64,
+                   M_DENSE_A = 128;
 
 // ---- counters.  cum[]: events whose date has passed (cumulative log columns); cur deltas are split in
 // "pre" (infection phase: part of the state the day log sees) and "post" (transition phase: after it)
@@ -76,7 +82,7 @@ struct DevTables {
     const uint32_t* rfx; const uint32_t* qfx; const double* W; const double* pool_hw;
     const uint32_t* od_thr; const double* stay_par; const uint32_t* dwell; const int32_t* znorm;
     const double* p_hosp; const double* p_crit; const double* p_hfat; const double* severe_risk;
-    const uint32_t* move_thr; const unsigned long long* sub_info; const int64_t* big_start;
+    const uint32_t* move_thr; const unsigned long long* sub_info; const int64_t* big_start; const uint32_t* omexp;
     int32_t D, A, P, hw_rows, n_big, step_ticks, mild_active;
     unsigned long long step_inv;    // floor(2^64 / step_ticks) + 1
     double symptomatic_rate, critical_fatality_rate;
@@ -86,15 +92,20 @@ struct DevTables {
 struct DevAgents {
     uint32_t* flags; uint32_t* aux;
     int32_t* t_infected; int32_t* t_contagious; int32_t* t_onset; int32_t* t_recovered; int32_t* t_return;
-    uint32_t* inf_at; const uint16_t* move_class; const uint32_t* econ_pool;
+    uint32_t* inf_at; const uint16_t* move_class; const uint32_t* econ_pool; const uint32_t* hh_index;
 };
 
+// Accumulators that every CTA adds to exist in `rep_mask + 1` replicas (a CTA uses replica
+// blockIdx & rep_mask): atomics on one address serialise in L2, and the hottest rows (the capital's
+// pool, the event tallies) would otherwise receive tens of thousands of them per launch.  The table
+// kernel sums the replicas.
 struct DevWork {
-    unsigned long long* acc;        // [2][P][A] of THIS sub-step: R fixed-point sums, then head counts
+    unsigned long long* acc;        // [replicas][2][P][A] of THIS sub-step: R fixed-point sums, then head counts
     const uint32_t* thr_out;        // [P][A] thresholds from the previous sub-step
     unsigned long long* hbig_read;  // [n_big] household hazard of big households, previous sub-step
     unsigned long long* hbig_write; // [n_big] accumulated this sub-step
-    unsigned long long* tally;      // [N_TALLY]
+    unsigned long long* tally;      // [replicas][N_TALLY]
+    uint32_t rep_mask;
 };
 
 struct StepArgs {
@@ -148,31 +159,23 @@ __device__ __forceinline__ uint32_t sample_quantile_u32(const uint32_t* __restri
     return (uint32_t)(lo + (((hi - lo) * g) >> 8));
 }
 
-// 1 - exp(-x), x >= 0: fixed sequence of IEEE double ops (oracle.one_minus_exp_neg).
-template <int N>
-__device__ __forceinline__ double horner_omexp(double y) {
-    double s = 1.0;
-#pragma unroll
-    for (int n = N; n > 1; --n) s = __dsub_rn(1.0, __dmul_rn(__dmul_rn(y, 1.0 / (double)n), s));
-    return __dmul_rn(y, s);
-}
-// Taylor order by range: 9 terms below 2^-5, 13 below 2^-2, 20 below 2^-1 (all to < 1 ulp of the series)
-__device__ __forceinline__ double one_minus_exp_neg(double x) {
-    x = fmin(x, 40.0);
-    if (x < 0.03125) return horner_omexp<9>(x);
-    if (x < 0.25) return horner_omexp<13>(x);
-    if (x < 0.5) return horner_omexp<20>(x);
-    double e = __dsub_rn(1.0, horner_omexp<20>(__dmul_rn(x, 0.015625)));
-#pragma unroll
-    for (int i = 0; i < 6; ++i) e = __dmul_rn(e, e);
-    return __dsub_rn(1.0, e);
-}
-__device__ __noinline__ uint32_t hazard_threshold(double x) {
-    return (uint32_t)ceil(__dmul_rn(one_minus_exp_neg(x), 2147483648.0));
+// 31-bit Bernoulli threshold ceil-ish((1 - exp(-h / 2^32)) * 2^31) of a hazard h given in units of 2^-32,
+// in integer arithmetic (oracle.hazard_threshold_fx): h = i / 256 + l with l < 2^-8,
+//   1 - exp(-h) = Q[i] + u - Q[i] u,  Q[i] = 1 - exp(-i / 256) (table, 0.32 fixed point),
+//   u = 1 - exp(-l) = l - l^2/2 + l^3/6  (remainder < 2^-36).
+__device__ __forceinline__ uint32_t hazard_threshold_fx(const uint32_t* __restrict__ omexp, unsigned long long h) {
+    if (h >= ((unsigned long long)ABM_OMEXP_N << 24)) return 0x80000000u;     // exp(-32) < 2^-46
+    const uint32_t i = (uint32_t)(h >> 24), l = (uint32_t)h & 0xFFFFFFu;
+    const unsigned long long q = __ldg(omexp + i);
+    const unsigned long long l2 = ((unsigned long long)l * l) >> 33;
+    const unsigned long long l3 = ((l2 * l) >> 32) / 3ull;
+    const unsigned long long u = (unsigned long long)l - l2 + l3;
+    const unsigned long long p = q + u - ((q * u) >> 32);
+    return (uint32_t)((p + 1ull) >> 1);
 }
 
 // sub-step index at which `date < now` first holds: floor(t / step) + 1, by multiply-high with
-// inv = floor(2^64 / step) + 1 (exact for every 32-bit t)
+// inv = floor(2^64 / step) + 1 (exact for every 32-bit t).  Monotone in t.
 __device__ __forceinline__ uint32_t fire_index(int32_t t, unsigned long long step_inv) {
     if (t == T_NEVER) return FIRE_NEVER;
     if (t < 0) return 0;
@@ -191,40 +194,45 @@ __device__ __forceinline__ int big_slot(const DevTables& T, int64_t cid) {
 
 __device__ __forceinline__ uint32_t loc_of(uint32_t f) { return (f >> F_LOC_SHIFT) & F_LOC_MASK; }
 __device__ __forceinline__ uint32_t set_loc(uint32_t f, uint32_t loc) { return (f & ~LOCF) | (loc << F_LOC_SHIFT); }
+__device__ __forceinline__ uint32_t status_of(uint32_t f) { return (f >> F_STATUS_SHIFT) & F_STATUS_MASK; }
+__device__ __forceinline__ uint32_t cur_of(uint32_t a) { return a & 0xFFFFu; }
+// index into the [2][128] rate tables: byte 2 of the flags = age | symptomatic << 7
+__device__ __forceinline__ uint32_t rate_index(uint32_t f) { return __byte_perm(f, 0u, 0x4442u); }
 
 // Outside pool (row of the district x status tables) the agent is currently in, or -1.
 // Hospital is location -current_district (base_model.py:270-272): district 0 maps onto its own outside
 // pool (quirk Q3); every other hospital / the dead location holds no susceptible agent.
-__device__ __forceinline__ int pool_of(const DevAgents& G, uint32_t f, uint32_t a, int64_t slot, int L0) {
+__device__ __forceinline__ int pool_of(const DevAgents& G, uint32_t f, uint32_t a, uint32_t slot, int L0) {
     const uint32_t kind = loc_of(f);
-    if (kind == LOC_CUR) return (int)(a >> 16);
     if (kind == LOC_HOMEPOOL) return L0;
+    if (kind == LOC_DEST) return (int)cur_of(a);
     if (kind == LOC_POOL) return (int)__ldg(G.econ_pool + slot);
-    if (kind == LOC_HOSP) return (a >> 16) == 0 ? 0 : -1;
+    if (kind == LOC_HOSP) return cur_of(a) == 0u ? 0 : -1;
     return -1;
 }
 // location an agent that goes about its economic activity ends up in (base_model.py:331-339, 346-352)
 __device__ __forceinline__ uint32_t econ_loc(uint32_t f) {
     const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
-    if (ek == EKIND_HOUSEHOLD) return LOC_HOME;
-    if (ek == EKIND_POOL) return LOC_POOL;
-    return (f & F_AWAY) ? LOC_HOMEPOOL : LOC_CUR;
+    return ek == EKIND_HOME_DISTRICT ? LOC_HOMEPOOL : (ek == EKIND_HOUSEHOLD ? LOC_HOME : LOC_POOL);
 }
-__device__ __forceinline__ uint32_t rate_index(uint32_t f) {
-    return ((((f >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) ? 128u : 0u) + ((f >> F_AGE_SHIFT) & F_AGE_MASK);
+// get_active_ids (base_model.py:198-209): (not hospitalised, or recovered) and at a non-negative location.
+// The location test is implied: hospital / dead locations only occur with clinical state >= 1 and an
+// epidemic state other than RECOVERED (recovery from hospital sends the agent home, base_model.py:246-250).
+__device__ __forceinline__ bool is_active(uint32_t f) {
+    return (f & CLINF) == 0u || (f & F_EPI_MASK) == EPI_R;
 }
 
 // ------------------------------------------------------------------------------------------------ infection event
 // Country.set_epidemic_status for one agent (base_model.py:838-1055).  Returns the new flags; writes the
-// cold vectors; the low half of `a` gets the sub-step at which the first scheduled event fires (>= k_first).
-// tally: shared (or global) int array indexed by the enum above.
+// cold vectors; the high half of `a` gets the sub-step at which the first scheduled event fires (>= k_first).
+// tally: shared (int) or global (unsigned long long) array indexed by the enum above.
 template <typename TallyT>
-__device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+__device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
                                                  int64_t cid, int32_t k_inf, int32_t now_inf, uint32_t k_first, TallyT* tally) {
     const U4 A4 = agent_draws(T, cid, k_inf, SITE_COURSE_A);
     const U4 B4 = agent_draws(T, cid, k_inf, SITE_COURSE_B);
     const uint32_t age = (f >> F_AGE_SHIFT) & F_AGE_MASK;
-    const uint32_t cur = a >> 16;
+    const uint32_t cur = cur_of(a);
     const bool sym = bernoulli(A4.x, T.symptomatic_rate);                                  // :853-857
     int32_t t_c, t_o, t_r;
     uint32_t out = 0;
@@ -256,15 +264,14 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
     G.t_onset[slot] = t_o;
     G.t_recovered[slot] = t_r;
     G.inf_at[slot] = (loc_of(f) << 16) | cur;                                               // :846-847
-    f &= ~(F_EPI_MASK | (F_SYM_MASK << F_SYM_SHIFT) | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
-    f |= EPI_I | ((sym ? 2u : 1u) << F_SYM_SHIFT) | out;                                    // :850
-    // earliest scheduled event (contagious always precedes the others except when onset < 12 h)
-    uint32_t fi = fire_index(t_c, T.step_inv);
-    const uint32_t fo = fire_index(t_o, T.step_inv), fr = fire_index(t_r, T.step_inv);
-    fi = fi < fo ? fi : fo;
-    fi = fi < fr ? fi : fr;
+    f &= ~(F_EPI_MASK | F_SYMPT | F_ASYMPT | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
+    f |= EPI_I | (sym ? F_SYMPT : F_ASYMPT) | out;                                          // :850
+    // earliest scheduled event: the one with the smallest date (fire_index is monotone)
+    int32_t first = t_c < t_o ? t_c : t_o;
+    first = first < t_r ? first : t_r;
+    uint32_t fi = fire_index(first, T.step_inv);
     fi = fi > k_first ? fi : k_first;
-    a = (a & 0xFFFF0000u) | fi;
+    a = (a & 0xFFFFu) | (fi << 16);
     return f;
 }
 
@@ -272,7 +279,7 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
 // update_agent_states (base_model.py:226-272) + contagious promotion (base_model.py:54-58) for one agent
 // whose next-event index is due.  Cumulative date counters are tallied the first time a date is passed;
 // the "current" counters of the day log move by the change of epidemic / clinical state.
-__device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, int64_t slot,
+__device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
                                                      int32_t now, int* s_tally) {
     const int32_t t_c = G.t_contagious[slot], t_o = G.t_onset[slot], t_r = G.t_recovered[slot];
     const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
@@ -306,21 +313,15 @@ __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const D
         if (clin == 1) atomicAdd(s_tally + POST_HOSPITALIZED, 1);
         if (clin == 2) atomicAdd(s_tally + POST_CRITICAL, 1);
     }
-    f = (f & ~(F_EPI_MASK | (F_CLIN_MASK << F_CLIN_SHIFT) | LOCF)) | epi | (clin << F_CLIN_SHIFT) | (loc << F_LOC_SHIFT);
-    uint32_t nf = FIRE_NEVER;
+    f = (f & ~(F_EPI_MASK | CLINF | LOCF)) | epi | (clin << F_CLIN_SHIFT) | (loc << F_LOC_SHIFT);
+    // next event = smallest date not yet passed (fire_index is monotone, so one evaluation suffices)
+    int32_t nxt = T_NEVER;
     const int32_t ts[6] = {t_c, t_o, t_h, t_cs, t_d, t_r};
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-        if (ts[i] >= now) { const uint32_t x = fire_index(ts[i], T.step_inv); nf = x < nf ? x : nf; }
-    a = (a & 0xFFFF0000u) | nf;
+        if (ts[i] >= now && ts[i] < nxt) nxt = ts[i];
+    a = (a & 0xFFFFu) | (fire_index(nxt, T.step_inv) << 16);
     return f;
-}
-
-__device__ __forceinline__ bool is_active(uint32_t f, uint32_t a) {
-    // get_active_ids (base_model.py:198-209): not hospitalised or recovered, at a non-negative location
-    const uint32_t epi = f & F_EPI_MASK, clin = (f >> F_CLIN_SHIFT) & F_CLIN_MASK, loc = loc_of(f);
-    const bool loc_ok = !(loc == LOC_DEAD || (loc == LOC_HOSP && (a >> 16) != 0));
-    return (clin < 1 || epi == EPI_R) && loc_ok;
 }
 
 // Length of stay for a traveller leaving `home` for `dest` on `weekday` (base_model.py:418-434): Gamma(mean^2/std,
@@ -359,50 +360,69 @@ __device__ __forceinline__ uint32_t od_destination(const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------ main kernel
 constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
 
-// iterate `BODY` over the agents whose bit is set in the per-lane `mask`; inside, J is the agent's
-// index 0..3 within the lane and fj / aj are its (mutable) flags / aux words
-#define ABM_FUNNEL(mask, ...)                                                        \
+// Funnel loops: iterate a body over the agents whose bit is set in the per-lane `mask`.  Inside, J is
+// the agent's index 0..3 within the lane and fj / aj are its flags / aux words (read-only in ABM_FUNNEL_RO,
+// written back with the dirty flags in ABM_FUNNEL_RW).
+#define ABM_FUNNEL_RO(mask, ...)                                                     \
+    while (__any_sync(FULL, (mask) != 0u)) {                                         \
+        if (mask) {                                                                  \
+            const int J = __ffs(mask) - 1;                                           \
+            (mask) &= (mask) - 1u;                                                   \
+            const uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));    \
+            const uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));    \
+            __VA_ARGS__                                                              \
+        }                                                                            \
+    }
+#define ABM_FUNNEL_RW(mask, ...)                                                     \
     while (__any_sync(FULL, (mask) != 0u)) {                                         \
         if (mask) {                                                                  \
             const int J = __ffs(mask) - 1;                                           \
             (mask) &= (mask) - 1u;                                                   \
             uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));          \
             uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));          \
-            const uint32_t fj_in = fj, aj_in = aj;                                   \
             __VA_ARGS__                                                              \
-            if (fj != fj_in) { dirty_f = true; if (J == 0) f0 = fj; else if (J == 1) f1 = fj; else if (J == 2) f2 = fj; else f3 = fj; } \
-            if (aj != aj_in) { dirty_a = true; if (J == 0) a0 = aj; else if (J == 1) a1 = aj; else if (J == 2) a2 = aj; else a3 = aj; } \
+            if (J == 0) { f0 = fj; a0 = aj; } else if (J == 1) { f1 = fj; a1 = aj; } \
+            else if (J == 2) { f2 = fj; a2 = aj; } else { f3 = fj; a3 = aj; }        \
+            dirty = true;                                                            \
         }                                                                            \
     }
 
 template <uint32_t MODE>
 __global__ void __launch_bounds__(THREADS)
 abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
-    __shared__ uint32_t s_hz[WARPS][2][SUB];          // per-warp household hazard sums (low / high 16-bit parts)
+    __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
+    __shared__ unsigned int s_acc[WARPS][2 * ABM_MAX_STATUS];   // per-warp home-pool pressure sums / head counts
     __shared__ int s_tally[N_TALLY];
-    __shared__ unsigned int s_cnt[ABM_MAX_STATUS], s_rlo[ABM_MAX_STATUS], s_rhi[ABM_MAX_STATUS];
+    __shared__ int s_home[WARPS];
+    __shared__ unsigned int s_done;
 
     const uint32_t mode = MODE == RUNTIME_MODE ? s.mode : ((MODE & ~M_WEEKDAY) | (s.mode & M_WEEKDAY));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < N_TALLY) s_tally[tid] = 0;
-    if (tid < ABM_MAX_STATUS) { s_cnt[tid] = 0; s_rlo[tid] = 0; s_rhi[tid] = 0; }
-    __syncthreads();
-
-    const int64_t sub = (int64_t)blockIdx.x * WARPS + wid;
+    const uint32_t sub = blockIdx.x * WARPS + wid;
     const unsigned long long info = __ldg(T.sub_info + sub);
     const int L0 = (int)(info >> 48);                                        // home district of every agent here
-    const int L0c = (int)(__ldg(T.sub_info + (int64_t)blockIdx.x * WARPS) >> 48);   // district of the CTA-level accumulators
     const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;     // canonical id of this lane's first slot
-    const int64_t slot0 = sub * SUB + lane * PER_LANE;
+    const uint32_t slot0 = sub * SUB + lane * PER_LANE;
     const int A = T.A;
 
     const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
     const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
+    // household index of each slot within the sub-tile (static, one byte per slot): issued with the hot
+    // words so the household phase does not wait for a dependent DRAM round trip
+    uint32_t ix = 0;
+    if (mode & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
+
+    if (tid < N_TALLY) s_tally[tid] = 0;
+    if (lane < 2 * ABM_MAX_STATUS) s_acc[wid][lane] = 0u;
+    if (lane == 0) s_home[wid] = L0;
+    if (tid == 0) s_done = 0u;
+    __syncthreads();
+
     uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
     uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
-    bool dirty_f = false, dirty_a = false;
-    uint32_t* hz_lo = s_hz[wid][0];
-    uint32_t* hz_hi = s_hz[wid][1];
+    bool dirty = false;
+    uint32_t* hz = s_hz[wid];
+    unsigned int* acc_w = s_acc[wid];
 
     // ================================================================ I(k-1): infection draws
     if (mode & M_INFECT) {
@@ -412,76 +432,72 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         const bool c0 = (f0 & CH_MASK) == CH_VAL, c1 = (f1 & CH_MASK) == CH_VAL, c2 = (f2 & CH_MASK) == CH_VAL,
                    c3 = (f3 & CH_MASK) == CH_VAL;
         if (__any_sync(FULL, c0 | c1 | c2 | c3)) {
-            // index of each slot's household within the sub-tile = number of household heads up to it - 1
-            const uint32_t h0 = (f0 >> 23) & 1u, h1 = (f1 >> 23) & 1u, h2 = (f2 >> 23) & 1u, h3 = (f3 >> 23) & 1u;
-            const uint32_t B0 = __ballot_sync(FULL, h0), B1 = __ballot_sync(FULL, h1), B2 = __ballot_sync(FULL, h2),
-                           B3 = __ballot_sync(FULL, h3);
-            const uint32_t lt = (1u << lane) - 1u;
-            const int before = __popc(B0 & lt) + __popc(B1 & lt) + __popc(B2 & lt) + __popc(B3 & lt) - 1;
-            const int i0 = before + (int)h0, i1 = i0 + (int)h1, i2 = i1 + (int)h2, i3 = i2 + (int)h3;
-            const int n_hh = __popc(B0) + __popc(B1) + __popc(B2) + __popc(B3);
-            *reinterpret_cast<uint4*>(hz_lo + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(hz_hi + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t i0 = ix & 0xFFu, i1 = (ix >> 8) & 0xFFu, i2 = (ix >> 16) & 0xFFu, i3 = ix >> 24;
+            const int n_hh = (int)((__shfl_sync(FULL, i3, 31) + 1u) & 0xFFu);   // 255 = headless run of a big household
+            *reinterpret_cast<uint4*>(hz + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             const uint32_t* q = T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0);
-            if (c0) { const uint32_t v = __ldg(q + rate_index(f0)); atomicAdd(hz_lo + i0, v & 0xFFFFu); atomicAdd(hz_hi + i0, v >> 16); }
-            if (c1) { const uint32_t v = __ldg(q + rate_index(f1)); atomicAdd(hz_lo + i1, v & 0xFFFFu); atomicAdd(hz_hi + i1, v >> 16); }
-            if (c2) { const uint32_t v = __ldg(q + rate_index(f2)); atomicAdd(hz_lo + i2, v & 0xFFFFu); atomicAdd(hz_hi + i2, v >> 16); }
-            if (c3) { const uint32_t v = __ldg(q + rate_index(f3)); atomicAdd(hz_lo + i3, v & 0xFFFFu); atomicAdd(hz_hi + i3, v >> 16); }
+            if (c0) atomicAdd(hz + i0, __ldg(q + rate_index(f0)));
+            if (c1) atomicAdd(hz + i1, __ldg(q + rate_index(f1)));
+            if (c2) atomicAdd(hz + i2, __ldg(q + rate_index(f2)));
+            if (c3) atomicAdd(hz + i3, __ldg(q + rate_index(f3)));
             __syncwarp();
-            for (int h = lane; h < n_hh; h += 32) {   // one threshold per exposed household
-                const uint32_t lo = hz_lo[h], hi = hz_hi[h];
-                uint32_t thr = 0;
-                if (lo | hi) {
-                    const unsigned long long hs = ((unsigned long long)hi << 16) + lo;
-                    thr = hazard_threshold(__dmul_rn((double)hs, 1.0 / 4294967296.0));
-                }
-                hz_lo[h] = thr;
-            }
+            for (int h = lane; h < n_hh; h += 32)     // one threshold per household (0 when nobody is contagious)
+                hz[h] = hazard_threshold_fx(T.omexp, (unsigned long long)hz[h] << 8);
             __syncwarp();
             constexpr uint32_t SH_VAL = EPI_S | (LOC_HOME << F_LOC_SHIFT);
-            if ((f0 & CH_MASK) == SH_VAL) t0 = hz_lo[i0];
-            if ((f1 & CH_MASK) == SH_VAL) t1 = hz_lo[i1];
-            if ((f2 & CH_MASK) == SH_VAL) t2 = hz_lo[i2];
-            if ((f3 & CH_MASK) == SH_VAL) t3 = hz_lo[i3];
+            if ((f0 & CH_MASK) == SH_VAL) t0 = hz[i0];
+            if ((f1 & CH_MASK) == SH_VAL) t1 = hz[i1];
+            if ((f2 & CH_MASK) == SH_VAL) t2 = hz[i2];
+            if ((f3 & CH_MASK) == SH_VAL) t3 = hz[i3];
         }
-        // ---- outside pools and big households
+        // ---- outside pools and big households: susceptible and not (at home in a small household).
+        // Home-district pool and trip destinations are one table look-up (predicated, all four agents);
+        // schools, the hospital of district 0 and big households are rare and go through the funnel.
         {
-            // susceptible and not (at home in a small household): loc != HOME, or BIGHH
-            const bool o0 = (f0 & F_EPI_MASK) == EPI_S && ((f0 & (LOCF | F_BIGHH)) != 0u);
-            const bool o1 = (f1 & F_EPI_MASK) == EPI_S && ((f1 & (LOCF | F_BIGHH)) != 0u);
-            const bool o2 = (f2 & F_EPI_MASK) == EPI_S && ((f2 & (LOCF | F_BIGHH)) != 0u);
-            const bool o3 = (f3 & F_EPI_MASK) == EPI_S && ((f3 & (LOCF | F_BIGHH)) != 0u);
-            if (__any_sync(FULL, o0 | o1 | o2 | o3)) {
+            constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT;
+            uint32_t odd = 0;
+            if (mode & M_DENSE_I) {
+                // daytime: almost everybody is in the outside pool of the home district -> row in registers
                 const uint32_t row_thr = lane < A ? __ldg(Wk.thr_out + L0 * A + lane) : 0u;
-                const uint32_t r0 = __shfl_sync(FULL, row_thr, (f0 >> F_STATUS_SHIFT) & F_STATUS_MASK);
-                const uint32_t r1 = __shfl_sync(FULL, row_thr, (f1 >> F_STATUS_SHIFT) & F_STATUS_MASK);
-                const uint32_t r2 = __shfl_sync(FULL, row_thr, (f2 >> F_STATUS_SHIFT) & F_STATUS_MASK);
-                const uint32_t r3 = __shfl_sync(FULL, row_thr, (f3 >> F_STATUS_SHIFT) & F_STATUS_MASK);
-                uint32_t odd = 0;     // agents in another pool than the home one, or in a big household
-#define ABM_OUT_THR(fj, aj, oj, rj, tj, bit)                                                        \
-                if (oj) {                                                                           \
-                    const uint32_t kind = loc_of(fj);                                               \
-                    if (kind == LOC_HOMEPOOL || (kind == LOC_CUR && (int)((aj) >> 16) == L0)) tj = rj; \
-                    else odd |= (bit);                                                              \
+                const uint32_t r0 = __shfl_sync(FULL, row_thr, status_of(f0)), r1 = __shfl_sync(FULL, row_thr, status_of(f1));
+                const uint32_t r2 = __shfl_sync(FULL, row_thr, status_of(f2)), r3 = __shfl_sync(FULL, row_thr, status_of(f3));
+#define ABM_OUT_THR(fj, aj, rj, tj, bit)                                                             \
+                if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
+                    const uint32_t lf = (fj) & LOCF;                                                 \
+                    if (lf == IN_HOMEPOOL) tj = rj;                                                  \
+                    else if (lf == IN_DEST) tj = __ldg(Wk.thr_out + cur_of(aj) * A + status_of(fj)); \
+                    else odd |= (bit);                                                               \
                 }
-                ABM_OUT_THR(f0, a0, o0, r0, t0, 1u)
-                ABM_OUT_THR(f1, a1, o1, r1, t1, 2u)
-                ABM_OUT_THR(f2, a2, o2, r2, t2, 4u)
-                ABM_OUT_THR(f3, a3, o3, r3, t3, 8u)
+                ABM_OUT_THR(f0, a0, r0, t0, 1u)
+                ABM_OUT_THR(f1, a1, r1, t1, 2u)
+                ABM_OUT_THR(f2, a2, r2, t2, 4u)
+                ABM_OUT_THR(f3, a3, r3, t3, 8u)
 #undef ABM_OUT_THR
-                ABM_FUNNEL(odd, {
-                    uint32_t thr = 0;
-                    if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
-                        const unsigned long long hzv = Wk.hbig_read[big_slot(T, cid0 + J)];
-                        if (hzv) thr = hazard_threshold(__dmul_rn((double)hzv, 1.0 / 4294967296.0));
-                    } else {
-                        const int pool = pool_of(G, fj, aj, slot0 + J, L0);
-                        if (pool >= 0) thr = __ldg(Wk.thr_out + pool * A + ((fj >> F_STATUS_SHIFT) & F_STATUS_MASK));
-                    }
-                    if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
-                })
+            } else {
+#define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
+                if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
+                    const uint32_t lf = (fj) & LOCF;                                                 \
+                    if (lf == IN_HOMEPOOL || lf == IN_DEST)                                          \
+                        tj = __ldg(Wk.thr_out + (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj)); \
+                    else odd |= (bit);                                                               \
+                }
+                ABM_OUT_THR(f0, a0, t0, 1u)
+                ABM_OUT_THR(f1, a1, t1, 2u)
+                ABM_OUT_THR(f2, a2, t2, 4u)
+                ABM_OUT_THR(f3, a3, t3, 8u)
+#undef ABM_OUT_THR
             }
+            ABM_FUNNEL_RO(odd, {
+                uint32_t thr = 0;
+                if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
+                    thr = hazard_threshold_fx(T.omexp, Wk.hbig_read[big_slot(T, cid0 + J)] << 8);
+                } else {
+                    const int pool = pool_of(G, fj, aj, slot0 + J, L0);
+                    if (pool >= 0) thr = __ldg(Wk.thr_out + pool * A + status_of(fj));
+                }
+                if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
+            })
         }
         // ---- the draw: one Philox block for the four agents of the lane
         uint32_t newly = 0;
@@ -491,7 +507,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                     ((X.w >> 1) < t3 ? 8u : 0u);
         }
         // ---- disease course of the newly infected
-        ABM_FUNNEL(newly, {
+        ABM_FUNNEL_RW(newly, {
             fj = infect_agent(T, G, fj, aj, slot0 + J, cid0 + J, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
             atomicAdd(s_tally + CUM_INFECTED, 1);
         })
@@ -500,52 +516,51 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     if (mode & M_STEP) {
         // ============================================================ T(k): due transitions
         {
-            const uint32_t k = (uint32_t)s.k;
-            uint32_t due = ((a0 & 0xFFFFu) <= k ? 1u : 0u) | ((a1 & 0xFFFFu) <= k ? 2u : 0u) | ((a2 & 0xFFFFu) <= k ? 4u : 0u) |
-                           ((a3 & 0xFFFFu) <= k ? 8u : 0u);
-            ABM_FUNNEL(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
+            const uint32_t lim = ((uint32_t)s.k << 16) | 0xFFFFu;      // fire index (high half of aux) <= k
+            uint32_t due = (a0 <= lim ? 1u : 0u) | (a1 <= lim ? 2u : 0u) | (a2 <= lim ? 4u : 0u) | (a3 <= lim ? 8u : 0u);
+            ABM_FUNNEL_RW(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
         }
 
         // ============================================================ M(k): movement (base_model.py:274-441)
         if (mode & M_GO_HOME) {                                                         // :274-302
             uint32_t away = 0;
-#define ABM_GO_HOME(fj, aj, bit)                                                                     \
-            if (is_active(fj, aj)) {                                                                 \
-                if (!((fj) & F_AWAY)) { const uint32_t nf = set_loc(fj, LOC_HOME); dirty_f |= nf != (fj); fj = nf; } \
-                else away |= (bit);                                                                  \
+#define ABM_GO_HOME(fj, bit)                                                                         \
+            if (is_active(fj)) {                                                                     \
+                if ((fj) & F_AWAY) away |= (bit);                                                    \
+                else if ((fj) & LOCF) { fj &= ~LOCF; dirty = true; }            /* LOC_HOME == 0 */  \
             }
-            ABM_GO_HOME(f0, a0, 1u)
-            ABM_GO_HOME(f1, a1, 2u)
-            ABM_GO_HOME(f2, a2, 4u)
-            ABM_GO_HOME(f3, a3, 8u)
+            ABM_GO_HOME(f0, 1u)
+            ABM_GO_HOME(f1, 2u)
+            ABM_GO_HOME(f2, 4u)
+            ABM_GO_HOME(f3, 8u)
 #undef ABM_GO_HOME
-            ABM_FUNNEL(away, {
+            ABM_FUNNEL_RW(away, {
                 if (G.t_return[slot0 + J] < s.now) {                                    // :285-293
-                    aj = (aj & 0xFFFFu) | ((uint32_t)L0 << 16);
-                    fj = set_loc(fj & ~F_AWAY, LOC_HOME);
+                    aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
+                    fj = fj & ~(F_AWAY | LOCF);
                 }
             })
         }
         if (mode & M_GO_OUT) {                                                          // :304-340
             const uint2 mc = *reinterpret_cast<const uint2*>(G.move_class + slot0);
-            const int col = (mode & M_WEEKDAY) ? 0 : 2;
+            const uint32_t* thr_col = T.move_thr + ((mode & M_WEEKDAY) ? 0 : 2);
             const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
             const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
             const U4 XM = group_draws(T, cid0, s.k, SITE_MOVER);
             uint32_t mover = 0, want_od = 0;
-#define ABM_MOVER(fj, aj, cls, xm, bit)                                                              \
-            if (is_active(fj, aj)) {                                                                 \
+#define ABM_MOVER(fj, cls, xm, bit)                                                                  \
+            if (is_active(fj)) {                                                                     \
                 const bool mild = T.mild_active && ((fj) & F_ONSET) && ((fj) & F_EPI_MASK) < EPI_R;   /* :212-219, :316 */ \
-                const uint32_t thr = __ldg(T.move_thr + 4u * (cls) + col + (mild ? 1 : 0));           \
+                const uint32_t thr = __ldg(thr_col + 4u * (cls) + (mild ? 1 : 0));                    \
                 if (((xm) >> 1) < thr) {                                                /* :317-318 a mover */ \
                     mover |= (bit);                                                                  \
                     if ((fj) & F_DMOVER) want_od |= (bit);                                           \
                 }                                                                                    \
             }
-            ABM_MOVER(f0, a0, mc.x & 0xFFFFu, XM.x, 1u)
-            ABM_MOVER(f1, a1, mc.x >> 16, XM.y, 2u)
-            ABM_MOVER(f2, a2, mc.y & 0xFFFFu, XM.z, 4u)
-            ABM_MOVER(f3, a3, mc.y >> 16, XM.w, 8u)
+            ABM_MOVER(f0, mc.x & 0xFFFFu, XM.x, 1u)
+            ABM_MOVER(f1, mc.x >> 16, XM.y, 2u)
+            ABM_MOVER(f2, mc.y & 0xFFFFu, XM.z, 4u)
+            ABM_MOVER(f3, mc.y >> 16, XM.w, 8u)
 #undef ABM_MOVER
             // district movers at home whose OD draw falls in the stay-home interval of their row, and movers
             // that are neither away nor district movers, just go about their economic activity
@@ -556,16 +571,16 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             if (mover & (bit)) {                                                                     \
                 const uint32_t u = (xo) >> 1;                                                        \
                 if (((fj) & F_AWAY) || (((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi))) trav |= (bit); \
-                else { const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty_f |= nf != (fj); fj = nf; } \
+                else { const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf; } \
             }
             ABM_GO_OUT(f0, XO.x, 1u)
             ABM_GO_OUT(f1, XO.y, 2u)
             ABM_GO_OUT(f2, XO.z, 4u)
             ABM_GO_OUT(f3, XO.w, 8u)
 #undef ABM_GO_OUT
-            ABM_FUNNEL(trav, {
+            ABM_FUNNEL_RW(trav, {
                 if ((fj & F_AWAY) && G.t_return[slot0 + J] < s.now) {                   // :342-360 back in the home district
-                    aj = (aj & 0xFFFFu) | ((uint32_t)L0 << 16);
+                    aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
                     fj &= ~F_AWAY;
                 }
                 bool left = false;
@@ -574,8 +589,8 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                     if (dest != (uint32_t)L0) {                                         // :410-439
                         const U4 XS = group_draws(T, cid0, s.k, SITE_STAY);
                         G.t_return[slot0 + J] = stay_return_tick(T, word_of(XS, J), s.weekday, (uint32_t)L0, dest, s.now);
-                        fj = set_loc(fj, LOC_CUR) | F_AWAY;
-                        aj = (aj & 0xFFFFu) | (dest << 16);
+                        fj = set_loc(fj, LOC_DEST) | F_AWAY;
+                        aj = (aj & 0xFFFF0000u) | dest;
                         left = true;
                     }
                 }
@@ -584,22 +599,29 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         }
 
         // ============================================================ A(k): pressure / headcount tables
-        unsigned long long* acc_r = Wk.acc;
-        unsigned long long* acc_n = Wk.acc + (size_t)T.P * A;
-        const bool cta_acc = L0 == L0c;      // this warp may use the CTA-level shared accumulators
-        uint32_t work = 0;                   // agents whose table contribution goes through the funnel
-        if (mode & M_DENSE) {
-            // most agents are in the outside pool of their home district: per-lane head counts in 4-bit
-            // fields (status 0..11), widened to bytes for three warp reductions
+        unsigned long long* acc_r = Wk.acc + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+        unsigned long long* acc_n = acc_r + (size_t)T.P * A;
+        // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
+        // destinations: predicated global adds.  Schools, the hospital of district 0 (quirk Q3) and
+        // contagious members of big households at home are rare and go through the funnel.
+        constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT, IN_POOL = LOC_POOL << F_LOC_SHIFT, IN_HOSP = LOC_HOSP << F_LOC_SHIFT;
+        constexpr uint32_t BH_MASK = F_EPI_MASK | LOCF | F_BIGHH, BH_VAL = EPI_C | F_BIGHH;
+        uint32_t work = 0;
+        if (mode & M_DENSE_A) {
+            // per-lane head counts in 4-bit fields (status 0..11), widened to bytes for three warp reductions
             unsigned long long cw = 0ull;
 #define ABM_COUNT(fj, aj, bit)                                                                       \
             {                                                                                        \
-                const uint32_t kind = loc_of(fj);                                                    \
-                const bool in_home_pool = kind == LOC_HOMEPOOL || (kind == LOC_CUR && (int)((aj) >> 16) == L0); \
-                const bool elsewhere = (kind == LOC_CUR && !in_home_pool) || kind == LOC_POOL || (kind == LOC_HOSP && ((aj) >> 16) == 0u); \
-                if (in_home_pool) cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);            \
+                const uint32_t lf = (fj) & LOCF;                                                     \
                 const bool cont = ((fj) & F_EPI_MASK) == EPI_C;                                      \
-                if (elsewhere || (cont && (in_home_pool || (((fj) & (LOCF | F_BIGHH)) == F_BIGHH)))) work |= (bit); \
+                if (lf == IN_HOMEPOOL) {                                                             \
+                    cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);                          \
+                    if (cont) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj)));        \
+                } else if (lf == IN_DEST) {                                                          \
+                    const uint32_t e = cur_of(aj) * A + status_of(fj);                               \
+                    atomicAdd(acc_n + e, 1ull);                                                      \
+                    if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+                } else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
             }
             ABM_COUNT(f0, a0, 1u)
             ABM_COUNT(f1, a1, 2u)
@@ -613,118 +635,170 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             if (lane < A) {
                 const uint32_t w = lane < 8 ? ((lane & 1) ? od : ev) : hi;
                 const uint32_t sh = lane < 8 ? 8u * (lane >> 1) : 8u * (((lane - 8) >> 1) + 2 * ((lane - 8) & 1));
-                const unsigned int v = (w >> sh) & 0xFFu;
-                if (v) {
-                    if (cta_acc) atomicAdd(s_cnt + lane, v);
-                    else atomicAdd(acc_n + (size_t)L0 * A + lane, (unsigned long long)v);
-                }
+                acc_w[ABM_MAX_STATUS + lane] += (w >> sh) & 0xFFu;       // this warp's own accumulator row
             }
         } else {
-#define ABM_SPARSE(fj, aj, bit)                                                                      \
+            // night: hardly anybody is in an outside pool
+#define ABM_COUNT(fj, aj, bit)                                                                       \
             {                                                                                        \
-                const uint32_t kind = loc_of(fj);                                                    \
-                const bool pooled = kind == LOC_CUR || kind == LOC_HOMEPOOL || kind == LOC_POOL || (kind == LOC_HOSP && ((aj) >> 16) == 0u); \
-                if (pooled || (((fj) & (F_EPI_MASK | LOCF | F_BIGHH)) == (EPI_C | F_BIGHH))) work |= (bit); \
+                const uint32_t lf = (fj) & LOCF;                                                     \
+                if (lf == IN_HOMEPOOL || lf == IN_DEST) {                                            \
+                    const uint32_t e = (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj); \
+                    atomicAdd(acc_n + e, 1ull);                                                      \
+                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+                } else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
             }
-            ABM_SPARSE(f0, a0, 1u)
-            ABM_SPARSE(f1, a1, 2u)
-            ABM_SPARSE(f2, a2, 4u)
-            ABM_SPARSE(f3, a3, 8u)
-#undef ABM_SPARSE
+            ABM_COUNT(f0, a0, 1u)
+            ABM_COUNT(f1, a1, 2u)
+            ABM_COUNT(f2, a2, 4u)
+            ABM_COUNT(f3, a3, 8u)
+#undef ABM_COUNT
         }
-        {
-            const bool dense = (mode & M_DENSE) != 0;
-            ABM_FUNNEL(work, {
-                const uint32_t st = (fj >> F_STATUS_SHIFT) & F_STATUS_MASK;
-                const bool cont = (fj & F_EPI_MASK) == EPI_C;
-                const int pool = pool_of(G, fj, aj, slot0 + J, L0);
-                if (pool >= 0) {
-                    const uint32_t kind = loc_of(fj);
-                    const bool counted = dense && (kind == LOC_HOMEPOOL || (kind == LOC_CUR && pool == L0));
-                    const uint32_t r = cont ? __ldg(T.rfx + rate_index(fj)) : 0u;
-                    if (pool == L0 && cta_acc) {
-                        if (!counted) atomicAdd(s_cnt + st, 1u);
-                        if (cont) { atomicAdd(s_rlo + st, r & 0xFFFFu); atomicAdd(s_rhi + st, r >> 16); }
-                    } else {
-                        if (!counted) atomicAdd(acc_n + (size_t)pool * A + st, 1ull);
-                        if (cont) atomicAdd(acc_r + (size_t)pool * A + st, (unsigned long long)r);
-                    }
-                } else if (cont && (fj & F_BIGHH) && loc_of(fj) == LOC_HOME) {
-                    const uint32_t qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0) + rate_index(fj));
-                    atomicAdd(Wk.hbig_write + big_slot(T, cid0 + J), (unsigned long long)qv);
-                }
-            })
-        }
+        ABM_FUNNEL_RO(work, {
+            const int pool = pool_of(G, fj, aj, slot0 + J, L0);
+            const bool cont = (fj & F_EPI_MASK) == EPI_C;
+            if (pool >= 0) {
+                const uint32_t e = (uint32_t)pool * A + status_of(fj);
+                atomicAdd(acc_n + e, 1ull);
+                if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
+            } else if (cont && (fj & (LOCF | F_BIGHH)) == F_BIGHH) {
+                const uint32_t qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0) + rate_index(fj));
+                atomicAdd(Wk.hbig_write + big_slot(T, cid0 + J), (unsigned long long)qv);
+            }
+        })
     }
 
     // ================================================================ write back what changed
-    if (dirty_f) *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
-    if (dirty_a) *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
-
-    __syncthreads();
-    if (tid < N_TALLY) {
-        const int v = s_tally[tid];
-        if (v) atomicAdd(Wk.tally + tid, (unsigned long long)(long long)v);
+    if (dirty) {
+        *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
+        *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
     }
-    if ((mode & M_STEP) && tid >= 32 && tid < 32 + A) {
-        const int b = tid - 32;
-        if (s_cnt[b]) atomicAdd(Wk.acc + (size_t)T.P * A + (size_t)L0c * A + b, (unsigned long long)s_cnt[b]);
-        const unsigned long long r = ((unsigned long long)s_rhi[b] << 16) + s_rlo[b];
-        if (r) atomicAdd(Wk.acc + (size_t)L0c * A + b, r);
+
+    // ================================================================ flush of the per-CTA counters by the last warp to finish
+    __threadfence_block();
+    unsigned int done = 0;
+    if (lane == 0) done = atomicAdd(&s_done, 1u);
+    done = __shfl_sync(FULL, done, 0);
+    if (done != WARPS - 1) return;
+    __threadfence_block();
+    if (lane < N_TALLY) {
+        const int v = s_tally[lane];
+        if (v) atomicAdd(Wk.tally + (size_t)(blockIdx.x & Wk.rep_mask) * N_TALLY + lane, (unsigned long long)(long long)v);
+    }
+    if ((mode & M_DENSE_A) && lane < 2 * ABM_MAX_STATUS) {
+        // lanes 0..11: pressure sums, lanes 12..23: head counts; consecutive warps of one home district are merged
+        const int b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
+        unsigned long long* dst = Wk.acc + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A);
+        unsigned long long sum = 0ull;
+        int home = s_home[0];
+        for (int w = 0; w < WARPS; ++w) {
+            const int hw = s_home[w];
+            if (hw != home) {
+                if (sum && b < A) atomicAdd(dst + (size_t)home * A + b, sum);
+                sum = 0ull; home = hw;
+            }
+            sum += s_acc[w][lane];
+        }
+        if (sum && b < A) atomicAdd(dst + (size_t)home * A + b, sum);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ table kernel
 // District x status tables -> infection thresholds:
-//   lambda[L][b] = hw[L] * (sum_a W[a][b] * R[L][a]) / Ncnt[L][b],  thr = ceil((1 - exp(-lambda)) * 2^31)
-// from the tables of the sub-step just executed; clears the other table buffer (used by the next
-// sub-step), folds the per-launch tallies into the running counters and, at log sub-steps, writes the
-// day-log row: cumulative date counters include this sub-step's transitions, the "current" counters are
-// taken before them (base_model.py:36-38: log_model_output runs before update_agent_states).
+//   lambda[L][b] = hw[L] * (sum_a W[a][b] * R[L][a]) / Ncnt[L][b],  thr = threshold(1 - exp(-lambda))
+// One block per outside pool L:
+//   reduce     sum the replicas of row L of the tables of the sub-step just executed into acc_sum and
+//              clear the row in every replica of the OTHER buffer (used by the next sub-step)
+//   threshold  thresholds of row L from acc_sum (after the all-reduce over ranks when there is one)
+// Block P (the last one) folds the per-launch tallies into the running counters and, at log sub-steps,
+// writes the day-log row: cumulative date counters include this sub-step's transitions, the "current"
+// counters are taken before them (base_model.py:36-38: log_model_output runs before update_agent_states).
 struct TableArgs {
+    int32_t do_reduce, do_threshold;
+    int32_t replicas;
     int32_t write_log;
     int32_t tick;
     long long seeds_before_now;
 };
 
-__global__ void abm_hazard_table_kernel(const DevTables T, const unsigned long long* acc, unsigned long long* acc_next,
-                                        uint32_t* thr_out, unsigned long long* hbig_clear, unsigned long long* tally,
-                                        long long* counters, long long* log_row, const TableArgs ta) {
-    const int n = T.P * T.A;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int L = i / T.A, b = i - L * T.A;
-        const unsigned long long cnt = acc[n + i];
-        uint32_t thr = 0;
-        if (cnt) {
-            double sum = 0.0;
-            for (int a = 0; a < T.A; ++a)
-                sum = __dadd_rn(sum, __dmul_rn(__ldg(T.W + a * T.A + b), (double)acc[L * T.A + a]));
-            const double lam = __dmul_rn(__ldg(T.pool_hw + L), __ddiv_rn(sum, (double)cnt));
-            thr = hazard_threshold(lam);
+constexpr int TABLE_THREADS = 256;
+
+__global__ void __launch_bounds__(TABLE_THREADS)
+abm_hazard_table_kernel(const DevTables T, const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ acc_next,
+                        unsigned long long* __restrict__ acc_sum, uint32_t* __restrict__ thr_out,
+                        unsigned long long* __restrict__ hbig_clear, unsigned long long* __restrict__ tally,
+                        long long* __restrict__ counters, long long* __restrict__ log_row, const TableArgs ta) {
+    __shared__ unsigned long long s_part[TABLE_THREADS / 32][32];
+    __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
+    const int A = T.A, n = T.P * A, t = threadIdx.x;
+    const int L = blockIdx.x;
+    if (L < T.P) {
+        // entry e < A: pressure sum of status e; A <= e < 2A: head count of status e - A
+        const int e = t & 31, g = t >> 5;
+        const size_t off = e < A ? (size_t)L * A + e : (size_t)n + (size_t)L * A + (e - A);
+        if (ta.do_reduce) {
+            unsigned long long v = 0ull;
+            if (e < 2 * A) {
+#pragma unroll 4
+                for (int r = g; r < ta.replicas; r += TABLE_THREADS / 32) {     // warp g sums every 8th replica
+                    v += acc[(size_t)r * 2 * n + off];
+                    acc_next[(size_t)r * 2 * n + off] = 0ull;
+                }
+            }
+            s_part[g][e] = v;
+            __syncthreads();
+            if (t < 2 * A) {
+                unsigned long long sum = 0ull;
+#pragma unroll
+                for (int w = 0; w < TABLE_THREADS / 32; ++w) sum += s_part[w][t];
+                acc_sum[off] = sum;
+                s_row[t] = sum;
+            }
+        } else if (t < 2 * A) {
+            s_row[t] = acc_sum[off];
         }
-        thr_out[i] = thr;
+        __syncthreads();
+        if (ta.do_threshold && t < A) {
+            const unsigned long long cnt = s_row[A + t];
+            uint32_t thr = 0;
+            if (cnt) {
+                double sum = 0.0;
+                for (int a = 0; a < A; ++a)
+                    sum = __dadd_rn(sum, __dmul_rn(__ldg(T.W + a * A + t), (double)s_row[a]));
+                const double lam = __dmul_rn(__ldg(T.pool_hw + L), __ddiv_rn(sum, (double)cnt));
+                const unsigned long long h = lam >= (double)(ABM_OMEXP_N >> 8) ? ((unsigned long long)ABM_OMEXP_N << 24)
+                                                                               : __double2ull_rz(__dmul_rn(lam, 4294967296.0));
+                thr = hazard_threshold_fx(T.omexp, h);
+            }
+            thr_out[L * A + t] = thr;
+        }
+        return;
     }
-    if (i < 2 * n) acc_next[i] = 0ull;
-    if (i < T.n_big) hbig_clear[i] = 0ull;
-    if (blockIdx.x == 0 && threadIdx.x < 12) {
-        const int t = threadIdx.x;
+    if (!ta.do_threshold) return;         // the bookkeeping below runs once per sub-step, with the thresholds
+    for (int i = t; i < T.n_big; i += blockDim.x) hbig_clear[i] = 0ull;
+    if (t < N_TALLY) {                    // fold the replicas of the tallies
+        unsigned long long v = 0ull;
+        for (int r = 0; r < ta.replicas; ++r) {
+            v += tally[(size_t)r * N_TALLY + t];
+            tally[(size_t)r * N_TALLY + t] = 0ull;
+        }
+        s_row[t] = v;
+    }
+    __syncthreads();
+    if (t < 12) {
         // counters[0..7] cumulative, counters[8..11] current exposed / contagious / hospitalised / critical
         long long v = counters[t];
         if (t < 8) {
-            v += (long long)tally[t];
-            tally[t] = 0ull;
+            v += (long long)s_row[t];
             counters[t] = v;
             if (ta.write_log) {
                 const int col = t < 6 ? t : (t == 6 ? ABM_C_ASYMPTOMATIC_COUNT : ABM_C_SYMPTOMATIC_COUNT);
                 log_row[col] = v + (t == CUM_INFECTED ? ta.seeds_before_now : 0);
             }
         } else {
-            v += (long long)tally[PRE_EXPOSED + (t - 8)];
+            v += (long long)s_row[PRE_EXPOSED + (t - 8)];
             if (ta.write_log) log_row[ABM_C_CURRENT_EXPOSED_CASES + (t - 8)] = v;
-            v += (long long)tally[POST_EXPOSED + (t - 8)];
-            tally[PRE_EXPOSED + (t - 8)] = 0ull;
-            tally[POST_EXPOSED + (t - 8)] = 0ull;
+            v += (long long)s_row[POST_EXPOSED + (t - 8)];
             counters[t] = v;
         }
         if (t == 0 && ta.write_log) log_row[ABM_C_TICK] = ta.tick;
@@ -755,7 +829,7 @@ __global__ void abm_district_sym_kernel(const DevTables T, const DevAgents G, in
     const uint32_t d = (uint32_t)(__ldg(T.sub_info + slot / SUB) >> 48);
     atomicAdd(pop + d, 1ull);
     const uint32_t epi = f & F_EPI_MASK;
-    if ((epi == EPI_I || epi == EPI_C) && ((f >> F_SYM_SHIFT) & F_SYM_MASK) == 2u) atomicAdd(sym + d, 1ull);
+    if ((epi == EPI_I || epi == EPI_C) && (f & F_SYMPT)) atomicAdd(sym + d, 1ull);
 }
 
 // current-state counters over all slots (abm_counters): an independent recount of what the running

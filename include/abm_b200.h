@@ -28,6 +28,7 @@ extern "C" {
 #define ABM_BIG_HOUSEHOLD 32     /* households above this size use the global-atomic path         */
 #define ABM_MAX_STATUS 12        /* economic statuses                                             */
 #define ABM_QN 4096              /* bins of the quantile tables                                    */
+#define ABM_OMEXP_N 8192         /* entries of the 1 - exp(-i/256) table (hazards up to 32)        */
 #define ABM_N_COUNTERS 12        /* fields of Country.log_model_output (base_model.py:1086-1104)   */
 #define ABM_LOG_STRIDE 16        /* int64 words per day-log row                                    */
 
@@ -86,9 +87,9 @@ typedef struct {
 
 /* Host pointers to the derived constant tables (abm_b200/tables.py); copied to the device. */
 typedef struct {
-    const uint32_t* rfx;          /* [2][128]  infection rate * 2^32 by (symptomatic, age)   params.py:236-242 */
-    const uint32_t* qfx;          /* [hw_rows][2][128]  -log(1 - 3 r hw) * 2^32              base_model.py:184-191 */
-    const double*   W;            /* [A][A]  k_a * M[a][b] * 2^-32                            params.py:278-297 */
+    const uint32_t* rfx;          /* [2][128]  infection rate * 2^24 by (symptomatic, age)   params.py:236-242 */
+    const uint32_t* qfx;          /* [hw_rows][2][128]  -log(1 - 3 r hw) * 2^24              base_model.py:184-191 */
+    const double*   W;            /* [A][A]  k_a * M[a][b] * 2^-24                            params.py:278-297 */
     const double*   pool_hw;      /* [P]     hand-washing multiplier of each outside pool               */
     const uint32_t* od_thr;       /* [7][D][D] ceil(cumulative OD prob * 2^31)                params.py:252-259 */
     const double*   stay_par;     /* [7][D][D][3] (mean h, a, b) of the stay transform        params.py:576-580 */
@@ -102,12 +103,13 @@ typedef struct {
     const uint64_t* sub_info;     /* [n_tiles * 8] per sub-tile: canonical id of slot 0 (multiple of 4) */
                                   /*   in bits 0..47, home district of its agents in bits 48..63        */
     const int64_t*  big_start;    /* [n_big_households+1] canonical id of first member (+ sentinel)     */
+    const uint32_t* omexp;        /* [ABM_OMEXP_N] round((1 - exp(-i/256)) * 2^32), the hazard -> probability table */
 } abm_tables;
 
 /* Device pointers of the caller-owned SoA agent store (Country's vectors, base_model.py:457-517). */
 typedef struct {
     uint32_t* flags;        /* [n_slots] packed state word                       */
-    uint32_t* aux;          /* [n_slots] next-event sub-step | current district  */
+    uint32_t* aux;          /* [n_slots] next-event sub-step << 16 | current district */
     int32_t*  t_infected;   /* date_infected                                     */
     int32_t*  t_contagious; /* date_start_contagious                             */
     int32_t*  t_onset;      /* date_start_symptomatic                            */
@@ -116,6 +118,7 @@ typedef struct {
     uint32_t* inf_at;       /* infected_at_{district,location}_ids               */
     const uint16_t* move_class; /* movement-probability class                    */
     const uint32_t* econ_pool;  /* outside pool of EKIND_POOL agents, may be NULL */
+    const uint8_t*  hh_index;   /* [n_slots] household index within the sub-tile  */
 } abm_agent_ptrs;
 
 /* Country.__init__ + EpidemicScheduler.__init__ (base_model.py:24-31, 445-525). */

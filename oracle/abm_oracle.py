@@ -40,9 +40,7 @@ TWO32 = 4294967296.0
 QBITS = 12
 QN = 1 << QBITS
 DAY = 1440
-INV = [0.0] + [1.0 / n for n in range(1, 24)]
-HAZARD_TERMS = 20
-HAZARD_CLAMP = 40.0
+OMEXP_N = 8192
 
 
 def u31(x):
@@ -65,28 +63,31 @@ def sample_quantile(table2, x):
     return np.where(i < QN - 1, main, tail)
 
 
-def one_minus_exp_neg(x):
-    """1 - exp(-x) for x >= 0 by a fixed sequence of IEEE double multiplies/adds (no FMA):
-    Taylor-Horner of order 9 / 13 / 20 below 2^-5 / 2^-2 / 2^-1, six squarings of exp(-x/64) above.
-    Mirrored op for op in CUDA (abm_kernels.cuh one_minus_exp_neg)."""
-    x = np.minimum(np.asarray(x, dtype=np.float64), HAZARD_CLAMP)
+def hazard_threshold_fx(omexp, h):
+    """31-bit Bernoulli threshold of the infection probability 1 - exp(-h / 2^32) for a hazard h given
+    in units of 2^-32 (uint64), in integer arithmetic -- mirrored op for op in CUDA
+    (abm_kernels.cuh hazard_threshold_fx): with h = i / 256 + l, l < 2^-8,
+        1 - exp(-h) = Q[i] + u - Q[i] u,   Q = omexp table,   u = l - l^2/2 + l^3/6."""
+    h = np.asarray(h, dtype=np.uint64)
+    big = h >= np.uint64(OMEXP_N << 24)
+    hh = np.where(big, np.uint64(0), h)
+    i = (hh >> np.uint64(24)).astype(np.int64)
+    l = hh & np.uint64(0xFFFFFF)
+    q = omexp[i].astype(np.uint64)
+    l2 = (l * l) >> np.uint64(33)
+    l3 = ((l2 * l) >> np.uint64(32)) // np.uint64(3)
+    u = l - l2 + l3
+    p = q + u - ((q * u) >> np.uint64(32))
+    thr = ((p + np.uint64(1)) >> np.uint64(1)).astype(np.uint32)
+    return np.where(big, np.uint32(0x80000000), thr).astype(np.uint32)
 
-    def horner(y, terms):
-        s = np.ones_like(y)
-        for n in range(terms, 1, -1):
-            s = 1.0 - (y * INV[n]) * s
-        return y * s
 
-    e = 1.0 - horner(x * 0.015625, 20)
-    for _ in range(6):
-        e = e * e
-    return np.where(x < 0.03125, horner(x, 9),
-                    np.where(x < 0.25, horner(x, 13), np.where(x < 0.5, horner(x, 20), 1.0 - e)))
-
-
-def hazard_threshold(x):
-    """31-bit Bernoulli threshold of the infection probability for hazard x."""
-    return np.ceil(one_minus_exp_neg(x) * TWO31).astype(np.uint32)
+def hazard_to_fx(lam):
+    """Hazard (float64 >= 0) -> units of 2^-32, truncated; saturates at the end of the omexp table."""
+    lam = np.asarray(lam, dtype=np.float64)
+    cap = float(OMEXP_N >> 8)
+    return np.where(lam >= cap, np.uint64(OMEXP_N << 24),
+                    np.floor(np.minimum(lam, cap) * TWO32).astype(np.uint64)).astype(np.uint64)
 
 
 class OracleModel:
@@ -286,7 +287,7 @@ class OracleModel:
             acc = acc + W[a][None, :] * rd[:, a][:, None]
         with np.errstate(divide='ignore', invalid='ignore'):
             lam = hw[:, None] * (acc / ncnt.astype(np.float64))
-        thr = hazard_threshold(np.where(ncnt > 0, lam, 0.0))
+        thr = hazard_threshold_fx(self.tab['omexp'], hazard_to_fx(np.where(ncnt > 0, lam, 0.0)))
         return np.where(ncnt > 0, thr, 0).astype(np.uint32)
 
     def household_hazard(self):
@@ -314,7 +315,7 @@ class OracleModel:
         h = np.nonzero(sus & at_home)[0]
         hs = hsum[loc[h] - self.D]
         exposed = hs > 0
-        thr[h[exposed]] = hazard_threshold(hs[exposed].astype(np.float64) * (1.0 / TWO32))
+        thr[h[exposed]] = hazard_threshold_fx(self.tab['omexp'], hs[exposed] << np.uint64(8))
         cand = np.nonzero(thr > 0)[0]
         x0 = philox.group_draws(self.seed, self.k, self.agent_ids[cand], philox.SITE_INFECT)
         newly = cand[(x0 >> np.uint32(1)) < thr[cand]]

@@ -17,8 +17,8 @@ def test_library_exports_all_declared_symbols(built_library):
 
 def test_python_structs_match_header_layout(built_library):
     from abm_b200 import engine
-    assert ct.sizeof(engine.AbmTables) == 15 * 8
-    assert ct.sizeof(engine.AbmAgentPtrs) == 10 * 8
+    assert ct.sizeof(engine.AbmTables) == 16 * 8
+    assert ct.sizeof(engine.AbmAgentPtrs) == 11 * 8
     assert engine.AbmConfig.seed.offset % 8 == 0 and engine.AbmConfig.stream.offset % 8 == 0
 
 
