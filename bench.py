@@ -53,54 +53,56 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread
+    (the timed region of a 15 M-agent run lasts tens of milliseconds, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _run(self):
+        nv, h = self._nvml, self._handle
+        bits = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get_reasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix='.csv')
-            os.close(fd)
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.index)],
-                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            self._nvml = nv
+            self._handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
         return self
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
 
     def summary(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if not self.path or not os.path.exists(self.path):
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        return out
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': float(self.max_mhz), 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -178,14 +180,17 @@ def run_cuda_arm(a):
     spec = synth.make_spec(n_districts=a.districts, R0=1.9, seed=POP_SEED)
     tab = tables.build_tables(spec)
     pop, base, dstart = sharding.make_synthetic_shard(n_total, spec, POP_SEED, world, rank)
-    uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None
     local_seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=POP_SEED + rank) + base
 
-    def make_sim():
-        sim = Simulation(spec, pop, seed=POP_SEED, device=local, tables=tab, max_days=a.spinup + a.warmup + a.steps + 8,
-                         agent_id_base=base, district_start=dstart, world_size=world, rank=rank, nccl_unique_id=uid)
-        sim.seed_infections(local_seeds)
-        return sim
+    from abm_b200.engine import HostStore
+    store = HostStore(spec, pop, agent_id_base=base)         # ingestion (slot map, bit packing, page-locking): untimed
+    max_days = a.spinup + a.warmup + a.steps + 16
+
+    def make_sim(upload=True):
+        uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None   # one id per communicator
+        return Simulation(spec, pop, seed=POP_SEED, device=local, tables=tab, max_days=max_days, agent_id_base=base,
+                          district_start=dstart, world_size=world, rank=rank, nccl_unique_id=uid, host_store=store,
+                          upload=upload)
 
     def barrier():
         if world > 1:
@@ -193,6 +198,7 @@ def run_cuda_arm(a):
         torch.cuda.synchronize(device)
 
     sim = make_sim()
+    sim.seed_infections(local_seeds)
     sim.step(a.spinup * SUBSTEPS_PER_DAY)
     for _ in range(a.warmup):
         sim.step(SUBSTEPS_PER_DAY)
@@ -201,10 +207,10 @@ def run_cuda_arm(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
-        e0.record()
+        e0.record(sim.stream)
         for _ in range(a.steps):
             sim.step(SUBSTEPS_PER_DAY)
-        e1.record()
+        e1.record(sim.stream)
         barrier()
     ms = e0.elapsed_time(e1)
     launches = sim.launch_count - launches0
@@ -213,7 +219,13 @@ def run_cuda_arm(a):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.item())
     value = n_total * a.steps / (ms / 1e3)
-    prevalence = sim.counters()
+
+    # ---- checkpoint of the state reached after the timed days (same epidemic regime for the e2e leg)
+    ckpt = sim.checkpoint()
+    prevalence = {name: int(ckpt['counters'][i]) for i, name in enumerate(
+        ['current_contagious_count', 'infected_count', 'hospitalized_count', 'critical_count', 'died_count', 'recovered_count',
+         'current_exposed_cases', 'current_contagious_cases', 'current_hospitalized_cases', 'current_critical_cases',
+         'asymptomatic_count', 'symptomatic_count'])}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream (live, same state)
     sim.set_profiling(True)
@@ -240,19 +252,24 @@ def run_cuda_arm(a):
                     kernel='abm_substep_kernel', avg_launch_ms=kms / klaunches, launches_timed=klaunches,
                     algorithmic_bytes_per_launch=per_launch_bytes,
                     peak_source='MEASURED_PEAKS.json (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
-                    own_layout_bytes_per_launch=8.0 * sim.sm.n_slots)
+                    own_layout_bytes_per_launch=8.0 * sim.sm.n_slots,
+                    whole_day_frac=ALGO_BYTES_PER_AGENT_DAY * pop.n / (ms / a.steps * 1e-3) / 1e9 / peak)
 
-    # ---- end to end through the public API with host buffers: upload the agent store from pinned host memory,
-    #      run the same K days reading each day's log row back, download the final state word
+    # ---- end to end through the public API with HOST buffers: the checkpointed agent store sits in page-locked
+    #      host memory; timed = upload of every per-agent vector + tables, K days with a log read-back per day,
+    #      download of the final packed state word
     e2e = None
     if not a.no_e2e:
         sim.close()
         del sim
+        pinned = {name: torch.from_numpy(arr).pin_memory() for name, arr in ckpt['arrays'].items()}
+        host_ckpt = dict(arrays=pinned, k=ckpt['k'], counters=ckpt['counters'], seeded=ckpt['seeded'])
         torch.cuda.synchronize(device)
         barrier()
         t0 = time.perf_counter()
-        sim = make_sim()                      # host -> device copies of every per-agent vector + tables
-        h2d = sum(v.numel() * v.element_size() for v in sim.buf.values())
+        sim = make_sim(upload=False)          # handle, device buffers, constant tables
+        sim.restore(host_ckpt)                # host -> device copy of every per-agent vector
+        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
         d2h = 0
         for _ in range(a.steps):
             sim.step(SUBSTEPS_PER_DAY)
@@ -268,8 +285,9 @@ def run_cuda_arm(a):
         wall = float(tw.item())
         e2e = dict(value=n_total * a.steps / wall, unit=UNIT, h2d_bytes_per_step=h2d / a.steps,
                    d2h_bytes_per_step=d2h / a.steps, seconds=wall,
-                   note='includes slot-map build, pinned upload of the whole agent store, seeding, K days with a log '
-                        'read-back per day, and the final state download (early-epidemic days: cheaper kernels)')
+                   note='K more days from the state the timed region ended in, through Simulation (C ABI) with the agent store in '
+                        'page-locked host memory: handle creation, table upload, host->device copy of all per-agent '
+                        'vectors, K days with a log read-back per day, device->host copy of the final state word')
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -284,7 +302,7 @@ def run_cuda_arm(a):
                                  f'{a.districts} districts, unmitigated R0=1.9, 4 h sub-steps (6 per simulated day), '
                                  f'household-aligned shards, NCCL all-reduce of the district x status tables per sub-step',
                         agents_total=n_total, spinup_days=a.spinup, seed_fraction=a.seed_fraction,
-                        l2=f'per-GPU inputs {h2d / 1e6 if not a.no_e2e else 34.0 * pop.n / 1e6:.0f} MB > 126 MB L2; the 8 B/agent hot record swept '
+                        l2=f'per-GPU agent store {store.nbytes / 1e6:.0f} MB > 126 MB L2; the 8 B/agent hot record swept '
                            f'every sub-step is {hot_mb:.0f} MB (no explicit flush: re-sweeping it is the workload)',
                         state_at_timing={k: prevalence[k] for k in ('current_exposed_cases', 'current_contagious_cases',
                                                                     'infected_count', 'recovered_count')}),

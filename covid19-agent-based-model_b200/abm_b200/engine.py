@@ -34,7 +34,7 @@ class AbmConfig(ct.Structure):
                 ('start_minute_of_day', ct.c_int32), ('start_weekday', ct.c_int32), ('mild_active', ct.c_int32),
                 ('max_log_rows', ct.c_int32), ('device', ct.c_int32), ('seed', ct.c_uint64),
                 ('symptomatic_rate', ct.c_double), ('critical_fatality_rate', ct.c_double), ('stream', ct.c_void_p),
-                ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
+                ('use_graph', ct.c_int32), ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
 
 
 class AbmTables(ct.Structure):
@@ -51,7 +51,7 @@ class AbmAgentPtrs(ct.Structure):
 
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
            'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
-           'abm_kernel_time', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
+           'abm_kernel_time', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
            'abm_version', 'abm_nccl_unique_id']
 
 _lib = None
@@ -82,6 +82,8 @@ def load_library(path=LIB_PATH):
     lib.abm_debug_tables.argtypes = [vp, vp, vp, vp]
     lib.abm_set_profiling.argtypes = [vp, ct.c_int32]
     lib.abm_kernel_time.argtypes = [vp, ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
+    lib.abm_get_state.argtypes = [vp, ct.POINTER(ct.c_int64), vp, ct.POINTER(ct.c_int64)]
+    lib.abm_set_state.argtypes = [vp, ct.c_int64, vp, ct.c_int64]
     lib.abm_current_step.argtypes = [vp]
     lib.abm_current_step.restype = ct.c_int64
     lib.abm_launch_count.argtypes = [vp]
@@ -100,6 +102,49 @@ def _ptr(a):
     return a.ctypes.data_as(ct.c_void_p)
 
 
+class HostStore:
+    """The agent store of one rank packed on the HOST (page-locked torch tensors), ready to upload.
+
+    This is what Country.load_agents / initialize_*_vectors (base_model.py:572-634, 760-799) produce: the
+    per-agent vectors in device layout.  Building it (slot map, bit packing) is ingestion work; uploading
+    it is a plain host -> device copy of `nbytes` bytes."""
+
+    def __init__(self, spec: ModelSpec, pop: Population, agent_id_base=0):
+        import torch
+        self.spec, self.pop, self.agent_id_base = spec, pop, int(agent_id_base)
+        self.sm = layout.build_slot_map(pop.household, pop.district, agent_id_base)
+        sm = self.sm
+        self.move_class, self.move_thr, _ = tables_mod.move_classes(pop, spec.mild_symptom_move_prob)
+        flags, aux = layout.pack_flags(pop, sm)
+        n_slots = sm.n_slots
+
+        def slots_from_agents(values, fill, dtype):
+            out = np.full(n_slots, fill, dtype=dtype)
+            out[sm.slot_of] = values
+            return out
+
+        never = np.int32(C.T_NEVER)
+        arrays = dict(
+            flags=flags.view(np.int32), aux=aux.view(np.int32),
+            t_infected=np.full(n_slots, never, np.int32), t_contagious=np.full(n_slots, never, np.int32),
+            t_onset=np.full(n_slots, never, np.int32), t_recovered=np.full(n_slots, never, np.int32),
+            t_return=np.full(n_slots, never, np.int32), inf_at=np.zeros(n_slots, np.int32),
+            move_class=slots_from_agents(self.move_class, 0, np.uint16).view(np.int16),
+            hh_index=layout.household_index(flags),
+        )
+        if pop.econ_pool is not None:
+            arrays['econ_pool'] = slots_from_agents(pop.econ_pool.astype(np.int32), 0, np.int32)
+        pin = torch.cuda.is_available()
+        self.host = {}
+        for k, a in arrays.items():
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            self.host[k] = t.pin_memory() if pin else t
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host.values())
+
+
 class Simulation:
     """One rank's share of the population on one GPU.
 
@@ -109,7 +154,8 @@ class Simulation:
     """
 
     def __init__(self, spec: ModelSpec, pop: Population, seed=0, device=0, tables=None, max_days=400,
-                 agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None):
+                 agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None, use_graph=True,
+                 host_store=None, upload=True):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('abm_b200 needs a CUDA device (no CPU fallback)')
@@ -118,36 +164,26 @@ class Simulation:
         self.spec, self.pop = spec, pop
         self.tab = tables if tables is not None else tables_mod.build_tables(spec)
         self.device = torch.device('cuda', device)
-        self.sm = layout.build_slot_map(pop.household, pop.district, agent_id_base)
+        torch.cuda.set_device(self.device)
+        # all device work of this simulation (uploads, kernels, graph replays) is ordered on one stream
+        self.stream = torch.cuda.Stream(device=self.device)
+        hs = host_store if host_store is not None else HostStore(spec, pop, agent_id_base)
+        if hs.pop is not pop or hs.agent_id_base != int(agent_id_base):
+            raise ValueError('host_store was built for another population / id base')
+        self.host_store = hs
+        self.sm = hs.sm
         sm = self.sm
         D = spec.n_districts
         if district_start is None:
             district_start = np.searchsorted(pop.district, np.arange(D + 1)).astype(np.int64) + agent_id_base
         self.district_start = np.ascontiguousarray(district_start, dtype=np.int64)
-        self.move_class, self.move_thr, _ = tables_mod.move_classes(pop, spec.mild_symptom_move_prob)
-        flags, aux = layout.pack_flags(pop, sm)
+        self.move_class, self.move_thr = hs.move_class, hs.move_thr
         n_slots = sm.n_slots
-
-        def dev(a):
-            # page-locked staging + asynchronous copy on the current stream
-            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(self.device, non_blocking=True)
-
-        def slots_from_agents(values, fill, dtype):
-            out = np.full(n_slots, fill, dtype=dtype)
-            out[sm.slot_of] = values
-            return out
-
-        never = np.int32(C.T_NEVER)
-        self.buf = dict(
-            flags=dev(flags.view(np.int32)), aux=dev(aux.view(np.int32)),
-            t_infected=dev(np.full(n_slots, never, np.int32)), t_contagious=dev(np.full(n_slots, never, np.int32)),
-            t_onset=dev(np.full(n_slots, never, np.int32)), t_recovered=dev(np.full(n_slots, never, np.int32)),
-            t_return=dev(np.full(n_slots, never, np.int32)), inf_at=dev(np.zeros(n_slots, np.int32)),
-            move_class=dev(slots_from_agents(self.move_class, 0, np.uint16).view(np.int16)),
-            hh_index=dev(layout.household_index(flags)),
-        )
-        if pop.econ_pool is not None:
-            self.buf['econ_pool'] = dev(slots_from_agents(pop.econ_pool.astype(np.int32), 0, np.int32))
+        with torch.cuda.stream(self.stream):      # asynchronous copies from page-locked memory
+            if upload:
+                self.buf = {k: t.to(self.device, non_blocking=True) for k, t in hs.host.items()}
+            else:                                 # the caller restores a checkpoint into the buffers
+                self.buf = {k: torch.empty(t.shape, dtype=t.dtype, device=self.device) for k, t in hs.host.items()}
 
         cfg = AbmConfig()
         cfg.n_slots, cfg.n_tiles, cfg.agent_id_base = n_slots, sm.n_tiles, agent_id_base
@@ -161,9 +197,8 @@ class Simulation:
         cfg.device = device
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.symptomatic_rate, cfg.critical_fatality_rate = self.tab['symptomatic_rate'], self.tab['critical_fatality_rate']
-        torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.current_stream(self.device)
         cfg.stream = self.stream.cuda_stream
+        cfg.use_graph = int(bool(use_graph))
         cfg.world_size, cfg.rank = world_size, rank
         self._uid = None
         if world_size > 1:
@@ -299,6 +334,27 @@ class Simulation:
     def state(self):
         """Reference-style vectors over this rank's agents (see layout.unpack_state)."""
         return layout.unpack_state(self.download(), self.pop, self.sm, self.spec.n_districts)
+
+    def checkpoint(self):
+        """Everything needed to resume: the agent vectors (numpy, slot order), the clock, the running
+        counters and the number of seeded infections.  Pending infection draws are applied first."""
+        k, seeded = ct.c_int64(), ct.c_int64()
+        counters = np.zeros(12, dtype=np.int64)
+        self._check(self.lib.abm_get_state(self.h, ct.byref(k), _ptr(counters), ct.byref(seeded)))
+        self.sync()
+        arrays = {name: v.cpu().numpy() for name, v in self.buf.items()}
+        return dict(arrays=arrays, k=int(k.value), counters=counters, seeded=int(seeded.value))
+
+    def restore(self, ckpt, arrays_on_device=False):
+        """Resume from `checkpoint()` output; `ckpt['arrays']` may hold numpy arrays or (pinned) torch tensors."""
+        torch = self.torch
+        if not arrays_on_device:
+            with torch.cuda.stream(self.stream):
+                for name, a in ckpt['arrays'].items():
+                    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+                    self.buf[name].copy_(t, non_blocking=True)
+        counters = np.ascontiguousarray(ckpt['counters'], dtype=np.int64)
+        self._check(self.lib.abm_set_state(self.h, int(ckpt['k']), _ptr(counters), int(ckpt['seeded'])))
 
     def set_profiling(self, on):
         self._check(self.lib.abm_set_profiling(self.h, int(bool(on))))

@@ -50,9 +50,16 @@ struct abm_handle {
     int32_t n_move_classes = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int64_t k = 0;                      // next sub-step to execute
+    DevClock* clock = nullptr;          // device-resident simulation clock (advanced by the table kernel)
+    int64_t k = 0;                      // host mirror: next sub-step to execute
     bool pending_infect = false;        // I(k-1) not applied yet
     int32_t n_log_rows = 0;
+    // one simulated day as a replayable CUDA graph
+    cudaGraphExec_t day_graph = nullptr;
+    int32_t graph_anchor_minute = -1;   // minute of day at which a replay may start
+    int32_t graph_logs = 0;             // log rows one replay writes
+    bool graph_failed = false;
+    int64_t graph_launches = 0;
     std::vector<SeedEvent> seeds;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -108,18 +115,23 @@ int alloc_zero(abm_handle* h, size_t count, Tp** dev_out) {
 }
 
 int32_t hour_of(const abm_config& c, int64_t tick) { return (int32_t)(((c.start_minute_of_day + tick) / 60) % 24); }
-int32_t weekday_of(const abm_config& c, int64_t tick) {
-    return (int32_t)((c.start_weekday + (c.start_minute_of_day + tick) / 1440) % 7);
+
+DevWork make_work(const abm_handle* h) {
+    DevWork w{};
+    w.acc2[0] = h->acc[0]; w.acc2[1] = h->acc[1];
+    w.thr_out = h->thr_out;
+    w.hbig2[0] = h->hbig[0]; w.hbig2[1] = h->hbig[1];
+    w.tally = h->tally;
+    w.acc_sum = h->acc_sum;
+    w.counters = h->counters;
+    w.daylog = h->daylog;
+    w.rep_mask = (uint32_t)h->replicas - 1u;
+    w.max_log_rows = h->cfg.max_log_rows;
+    return w;
 }
 
-int launch_main(abm_handle* h, const StepArgs& s) {
-    DevWork w{};
-    w.acc = h->acc[s.k & 1];
-    w.thr_out = h->thr_out;
-    w.hbig_write = h->hbig[s.k & 1];
-    w.hbig_read = h->hbig[(s.k + 1) & 1];
-    w.tally = h->tally;
-    w.rep_mask = (uint32_t)h->replicas - 1u;
+int launch_main(abm_handle* h, uint32_t mode) {
+    const DevWork w = make_work(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->prof_used == h->prof_events.size()) {
@@ -133,9 +145,9 @@ int launch_main(abm_handle* h, const StepArgs& s) {
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
     const dim3 grid((unsigned)h->cfg.n_tiles), block(THREADS);
-    const uint32_t m = s.mode & ~(M_WEEKDAY | M_LOG);
+    const uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
-#define ABM_LAUNCH(MODE) abm_substep_kernel<MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, s)
+#define ABM_LAUNCH(MODE) abm_substep_kernel<MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, h->clock, m)
     if (m == (M_INFECT | M_STEP)) ABM_LAUNCH(M_INFECT | M_STEP);                                        // night
     else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A);   // day
     else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
@@ -145,7 +157,96 @@ int launch_main(abm_handle* h, const StepArgs& s) {
 #undef ABM_LAUNCH
     if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches++;
+    return ABM_OK;
+}
+
+// What the next sub-step does, from the host mirror of the clock (EpidemicScheduler.step, base_model.py:33-58).
+struct SubstepPlan { uint32_t mode; bool log; };
+
+SubstepPlan plan_substep(const abm_config& c, int64_t k, bool pending_infect, bool& daytime) {
+    const int64_t tick = k * c.step_ticks;
+    const int32_t hour = hour_of(c, tick);
+    SubstepPlan p{};
+    p.mode = M_STEP | (pending_infect ? M_INFECT : 0u);
+    if (daytime && pending_infect) p.mode |= M_DENSE_I;           // the draw applied now belongs to a daytime sub-step
+    if (hour == 8) { p.mode |= M_GO_OUT; daytime = true; }        // params.py:131,135
+    if (hour == 16) { p.mode |= M_GO_HOME; daytime = false; }     // params.py:132,136
+    if (daytime) p.mode |= M_DENSE_A;
+    p.log = hour == 8;                                            // base_model.py:1083
+    if (p.log) p.mode |= M_LOG;
+    return p;
+}
+
+// Enqueue one sub-step: the agent kernel, then the table kernel(s) (with the all-reduce over ranks between
+// the replica sum and the thresholds when there are several ranks).  Everything time-dependent is read
+// from the device clock, so the same sequence can be captured into a graph.
+int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
+    const abm_config& c = h->cfg;
+    const int pa = c.n_pools * c.n_status;
+    int rc = launch_main(h, p.mode);
+    if (rc) return rc;
+    const DevWork w = make_work(h);
+    TableArgs ta{};
+    ta.replicas = h->replicas;
+    ta.write_log = p.log ? 1 : 0;
+    if (h->comm) {
+        ta.do_reduce = 1; ta.do_threshold = 0;
+        abm_hazard_table_kernel<<<c.n_pools, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        ncclResult_t r = h->nccl_allreduce(h->acc_sum, h->acc_sum, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
+        ta.do_reduce = 0; ta.do_threshold = 1;
+        abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        *launches += 3;
+    } else {
+        ta.do_reduce = 1; ta.do_threshold = 1;
+        abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        *launches += 2;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return ABM_OK;
+}
+
+int check_limits(abm_handle* h, int64_t k_after, int32_t logs_after) {
+    const abm_config& c = h->cfg;
+    if (k_after >= 0xFFF0) return fail(h, ABM_ERR_STATE, "sub-step index exceeds the 16-bit event field");
+    if ((k_after + 2) * c.step_ticks >= 0x7FFFFFFF) return fail(h, ABM_ERR_STATE, "tick overflow");
+    if (logs_after > c.max_log_rows) return fail(h, ABM_ERR_STATE, "day log full (%d rows)", c.max_log_rows);
+    return ABM_OK;
+}
+
+// Capture the next `steps_per_day` sub-steps into a graph.  Valid whenever the simulation is in its periodic
+// regime (an infection draw pending, at least one full day executed) and starts at the same minute of day.
+int build_day_graph(abm_handle* h) {
+    const abm_config& c = h->cfg;
+    const int spd = 1440 / c.step_ticks;
+    bool daytime = h->daytime;
+    cudaGraph_t graph = nullptr;
+    int64_t launches = 0;
+    int logs = 0;
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGetLastError(); h->graph_failed = true; return ABM_OK; }
+    int rc = ABM_OK;
+    const bool was_profiling = h->profiling;
+    h->profiling = false;
+    for (int i = 0; i < spd && rc == ABM_OK; ++i) {
+        const SubstepPlan p = plan_substep(c, h->k + i, true, daytime);
+        logs += p.log ? 1 : 0;
+        rc = enqueue_substep(h, p, &launches);
+    }
+    h->profiling = was_profiling;
+    e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != ABM_OK || e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        h->graph_failed = true;          // fall back to plain launches for the rest of the run
+        return ABM_OK;
+    }
+    e = cudaGraphInstantiate(&h->day_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); h->day_graph = nullptr; h->graph_failed = true; return ABM_OK; }
+    h->graph_anchor_minute = (int32_t)((c.start_minute_of_day + h->k * c.step_ticks) % 1440);
+    h->graph_logs = logs;
+    h->graph_launches = launches;
     return ABM_OK;
 }
 
@@ -201,7 +302,11 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(h, ABM_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
     CUDA_TRY(h, cudaSetDevice(cfg->device));
-    h->stream = (cudaStream_t)cfg->stream;   // NULL is the legacy default stream, which is also torch's default
+    h->stream = (cudaStream_t)cfg->stream;
+    if (!h->stream) {                        // the legacy default stream cannot be captured into a graph
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
     const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
     int rc;
     // replicas of the accumulators: a power of two <= 64 keeping each table buffer under 8 MiB
@@ -215,6 +320,14 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[1]))) return rc;
     if ((rc = alloc_zero(h, (size_t)h->replicas * N_TALLY, &h->tally))) return rc;
     if ((rc = alloc_zero(h, (size_t)12, &h->counters))) return rc;
+    if ((rc = alloc_zero(h, (size_t)1, &h->clock))) return rc;
+    {
+        DevClock clk{};
+        clk.k = 0; clk.now = 0; clk.minute_abs = cfg->start_minute_of_day; clk.weekday0 = cfg->start_weekday;
+        clk.weekday = (cfg->start_weekday + cfg->start_minute_of_day / 1440) % 7;
+        CUDA_TRY(h, cudaMemcpyAsync(h->clock, &clk, sizeof clk, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     if ((rc = alloc_zero(h, (size_t)(cfg->max_log_rows + 1) * ABM_LOG_STRIDE, &h->daylog))) return rc;
     if (cfg->world_size > 1) {
         if (!cfg->nccl_unique_id) return fail(h, ABM_ERR_ARG, "world_size > 1 needs an ncclUniqueId");
@@ -302,6 +415,10 @@ int abm_refresh(abm_handle* h, const uint32_t* move_thr, int32_t n_move_classes)
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         h->T.move_thr = mt;
         h->n_move_classes = n_move_classes;
+        if (h->day_graph) {              // kernel arguments are baked into the captured day: capture again
+            cudaGraphExecDestroy(h->day_graph);
+            h->day_graph = nullptr;
+        }
     }
     return ABM_OK;
 }
@@ -318,7 +435,7 @@ int abm_seed(abm_handle* h, const int64_t* slots, const int64_t* ids, int64_t n)
     CUDA_TRY(h, cudaMemcpyAsync(d_slots, slots, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(d_ids, ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     const int32_t now = (int32_t)(h->k * h->cfg.step_ticks);
-    abm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->T, h->G, h->tally, d_slots, d_ids, n, (int32_t)h->k, now);
+    abm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->T, h->G, h->tally, h->clock, d_slots, d_ids, n);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d_slots);
@@ -332,60 +449,42 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
     if (!h || n_substeps < 0) return ABM_ERR_ARG;
     if (!h->have_tables || !h->have_agents) return fail(h, ABM_ERR_STATE, "tables / agents not set");
     const abm_config& c = h->cfg;
-    const int pa = c.n_pools * c.n_status;
-    for (int32_t i = 0; i < n_substeps; ++i) {
-        if (h->k >= 0xFFF0) return fail(h, ABM_ERR_STATE, "sub-step index exceeds the 16-bit event field");
-        const int64_t tick = h->k * c.step_ticks;
-        if (tick + 2 * c.step_ticks >= 0x7FFFFFFF) return fail(h, ABM_ERR_STATE, "tick overflow");
-        const int32_t hour = hour_of(c, tick), wd = weekday_of(c, tick);
-        StepArgs s{};
-        s.k = (int32_t)h->k; s.now = (int32_t)tick; s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks; s.weekday = wd;
-        s.mode = M_STEP | (h->pending_infect ? M_INFECT : 0u);
-        if (h->daytime && h->pending_infect) s.mode |= M_DENSE_I;     // the draw applied now belongs to a daytime sub-step
-        if (hour == 8) { s.mode |= M_GO_OUT; h->daytime = true; }     // params.py:131,135
-        if (hour == 16) { s.mode |= M_GO_HOME; h->daytime = false; }  // params.py:132,136
-        if (h->daytime) s.mode |= M_DENSE_A;
-        if (wd <= 4) s.mode |= M_WEEKDAY;             // base_model.py:309
-        const bool log = hour == 8;                   // base_model.py:1083
-        long long* row = h->daylog + (size_t)c.max_log_rows * ABM_LOG_STRIDE;   // scratch row
-        if (log) {
-            if (h->n_log_rows >= c.max_log_rows) return fail(h, ABM_ERR_STATE, "day log full (%d rows)", c.max_log_rows);
-            s.mode |= M_LOG;
-            row = h->daylog + (size_t)h->n_log_rows * ABM_LOG_STRIDE;
+    const bool periodic = 1440 % c.step_ticks == 0;
+    const int spd = periodic ? 1440 / c.step_ticks : 0;
+    int32_t left = n_substeps;
+    while (left > 0) {
+        // whole simulated days in the periodic regime replay the captured graph
+        if (periodic && c.use_graph && !h->graph_failed && !h->profiling && h->pending_infect && left >= spd && h->k >= spd) {
+            if (!h->day_graph) {
+                int rc = build_day_graph(h);
+                if (rc) return rc;
+            }
+            const int32_t minute = (int32_t)((c.start_minute_of_day + h->k * c.step_ticks) % 1440);
+            if (h->day_graph && minute == h->graph_anchor_minute) {
+                int rc = check_limits(h, h->k + spd, h->n_log_rows + h->graph_logs);
+                if (rc) return rc;
+                CUDA_TRY(h, cudaGraphLaunch(h->day_graph, h->stream));
+                bool daytime = h->daytime;
+                for (int i = 0; i < spd; ++i) plan_substep(c, h->k + i, true, daytime);
+                h->daytime = daytime;
+                h->k += spd;
+                h->n_log_rows += h->graph_logs;
+                h->launches += h->graph_launches;
+                left -= spd;
+                continue;
+            }
         }
-        int rc = launch_main(h, s);
+        bool daytime = h->daytime;
+        const SubstepPlan p = plan_substep(c, h->k, h->pending_infect, daytime);
+        int rc = check_limits(h, h->k + 1, h->n_log_rows + (p.log ? 1 : 0));
         if (rc) return rc;
-        TableArgs ta{};
-        ta.replicas = h->replicas;
-        ta.write_log = log ? 1 : 0;
-        ta.tick = (int32_t)tick;
-        ta.seeds_before_now = 0;
-        for (const SeedEvent& e : h->seeds)
-            if (e.tick < tick) ta.seeds_before_now += e.n;
-        unsigned long long* acc = h->acc[s.k & 1];
-        unsigned long long* acc_next = h->acc[(s.k + 1) & 1];
-        unsigned long long* hbig_next = h->hbig[(s.k + 1) & 1];
-        if (h->comm) {
-            // sum the replicas, sum over ranks, then derive the thresholds from the global tables
-            ta.do_reduce = 1; ta.do_threshold = 0;
-            abm_hazard_table_kernel<<<c.n_pools, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
-                                                                     h->tally, h->counters, row, ta);
-            ncclResult_t r = h->nccl_allreduce(h->acc_sum, h->acc_sum, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
-            if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
-            ta.do_reduce = 0; ta.do_threshold = 1;
-            abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
-                                                                         h->tally, h->counters, row, ta);
-            h->launches += 2;
-        } else {
-            ta.do_reduce = 1; ta.do_threshold = 1;
-            abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, acc, acc_next, h->acc_sum, h->thr_out, hbig_next,
-                                                                         h->tally, h->counters, row, ta);
-            h->launches += 1;
-        }
-        CUDA_TRY(h, cudaGetLastError());
-        if (log) h->n_log_rows++;
+        rc = enqueue_substep(h, p, &h->launches);
+        if (rc) return rc;
+        h->daytime = daytime;
+        if (p.log) h->n_log_rows++;
         h->k++;
         h->pending_infect = true;
+        left--;
     }
     return ABM_OK;
 }
@@ -393,13 +492,9 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
 int abm_flush(abm_handle* h) {
     if (!h) return ABM_ERR_ARG;
     if (!h->pending_infect) return ABM_OK;
-    const abm_config& c = h->cfg;
-    StepArgs s{};
-    s.k = (int32_t)h->k; s.now = (int32_t)(h->k * c.step_ticks); s.k_inf = s.k - 1; s.now_inf = s.now - c.step_ticks;
-    s.weekday = weekday_of(c, s.now);
-    s.mode = M_INFECT | (h->daytime ? M_DENSE_I : 0u);
-    int rc = launch_main(h, s);
+    int rc = launch_main(h, M_INFECT | (h->daytime ? M_DENSE_I : 0u));
     if (rc) return rc;
+    h->launches++;
     h->pending_infect = false;
     return ABM_OK;
 }
@@ -511,6 +606,54 @@ int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches) {
     return ABM_OK;
 }
 
+int abm_get_state(abm_handle* h, int64_t* k, int64_t counters[ABM_N_COUNTERS], int64_t* seeded) {
+    if (!h || !k || !counters || !seeded) return ABM_ERR_ARG;
+    int rc = abm_counters(h, counters);          // flushes the pending infection draws
+    if (rc) return rc;
+    *k = h->k;
+    *seeded = 0;
+    for (const SeedEvent& e : h->seeds) *seeded += e.n;
+    return ABM_OK;
+}
+
+int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTERS], int64_t seeded) {
+    if (!h || !counters || k < 0 || k >= 0xFFF0) return ABM_ERR_ARG;
+    const abm_config& c = h->cfg;
+    // running counters in the library's order: 8 cumulative, then the 4 current ones
+    long long run[12];
+    run[CUM_CONTAGIOUS] = counters[ABM_C_CURRENT_CONTAGIOUS_COUNT];
+    run[CUM_INFECTED] = counters[ABM_C_INFECTED_COUNT] - seeded;
+    run[CUM_HOSPITALIZED] = counters[ABM_C_HOSPITALIZED_COUNT];
+    run[CUM_CRITICAL] = counters[ABM_C_CRITICAL_COUNT];
+    run[CUM_DIED] = counters[ABM_C_DIED_COUNT];
+    run[CUM_RECOVERED] = counters[ABM_C_RECOVERED_COUNT];
+    run[CUM_ASYM] = counters[ABM_C_ASYMPTOMATIC_COUNT];
+    run[CUM_SYM] = counters[ABM_C_SYMPTOMATIC_COUNT];
+    for (int i = 0; i < 4; ++i) run[8 + i] = counters[ABM_C_CURRENT_EXPOSED_CASES + i];
+    DevClock clk{};
+    clk.k = (int32_t)k; clk.now = (int32_t)(k * c.step_ticks);
+    clk.minute_abs = c.start_minute_of_day + clk.now; clk.weekday0 = c.start_weekday;
+    clk.weekday = (c.start_weekday + clk.minute_abs / 1440) % 7;
+    clk.n_log_rows = 0; clk.seeds_before = seeded; clk.seeds_at_now = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->clock, &clk, sizeof clk, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->counters, run, sizeof run, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->tally, 0, (size_t)h->replicas * N_TALLY * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->k = k;
+    h->n_log_rows = 0;
+    h->pending_infect = false;
+    h->seeds.clear();
+    if (seeded) h->seeds.push_back(SeedEvent{-1, seeded});
+    // who is out and about follows from the hour: go_out at 8, go_home at 16 (params.py:131-136)
+    h->daytime = false;
+    for (int64_t j = k - 1; j >= 0 && j > k - 1 - 1440 / c.step_ticks - 1; --j) {
+        const int32_t hour = hour_of(c, j * c.step_ticks);
+        if (hour == 8) { h->daytime = true; break; }
+        if (hour == 16) { h->daytime = false; break; }
+    }
+    return ABM_OK;
+}
+
 int64_t abm_current_step(abm_handle* h) { return h ? h->k : -1; }
 int64_t abm_launch_count(abm_handle* h) { return h ? h->launches : -1; }
 
@@ -518,6 +661,7 @@ void abm_destroy(abm_handle* h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
+    if (h->day_graph) cudaGraphExecDestroy(h->day_graph);
     for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (void* p : h->owned) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

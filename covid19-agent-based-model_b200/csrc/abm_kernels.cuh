@@ -100,12 +100,28 @@ struct DevAgents {
 // pool, the event tallies) would otherwise receive tens of thousands of them per launch.  The table
 // kernel sums the replicas.
 struct DevWork {
-    unsigned long long* acc;        // [replicas][2][P][A] of THIS sub-step: R fixed-point sums, then head counts
-    const uint32_t* thr_out;        // [P][A] thresholds from the previous sub-step
-    unsigned long long* hbig_read;  // [n_big] household hazard of big households, previous sub-step
-    unsigned long long* hbig_write; // [n_big] accumulated this sub-step
+    unsigned long long* acc2[2];    // [replicas][2][P][A] each: R fixed-point sums, then head counts; sub-step k uses acc2[k & 1]
+    uint32_t* thr_out;              // [P][A] thresholds from the previous sub-step
+    unsigned long long* hbig2[2];   // [n_big] household hazard of big households: written at k into hbig2[k & 1], read from the other
     unsigned long long* tally;      // [replicas][N_TALLY]
+    unsigned long long* acc_sum;    // [2][P][A] replicas (and ranks) summed: tables of the last sub-step
+    long long* counters;            // [12] running cumulative (0..7) and current (8..11) counters
+    long long* daylog;              // [max_log_rows + 1][ABM_LOG_STRIDE]
     uint32_t rep_mask;
+    int32_t max_log_rows;
+};
+
+// The simulation clock lives in device memory and is advanced by the table kernel, so a whole simulated
+// day (6 x [sub-step kernel, table kernel]) is one replayable CUDA graph with no per-launch arguments.
+struct __align__(16) DevClock {
+    int32_t k;            // next sub-step to execute
+    int32_t now;          // its minute tick
+    int32_t weekday;      // 0..6 of `now`
+    int32_t minute_abs;   // start_minute_of_day + now
+    int32_t weekday0;     // weekday of tick 0's day
+    int32_t n_log_rows;
+    long long seeds_before;   // seeded infections with tick < now     (base_model.py:796 + :1090)
+    long long seeds_at_now;   // seeded at the current tick
 };
 
 struct StepArgs {
@@ -116,6 +132,14 @@ struct StepArgs {
     uint32_t mode;
     int32_t weekday;  // 0..6 of `now`
 };
+__device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock* __restrict__ clk, uint32_t mode) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(clk));           // k, now, weekday, minute_abs
+    StepArgs s;
+    s.k = c.x; s.now = c.y; s.k_inf = s.k - 1; s.now_inf = s.now - T.step_ticks;
+    s.weekday = c.z;
+    s.mode = mode | (s.weekday <= 4 ? M_WEEKDAY : 0u);       // base_model.py:309
+    return s;
+}
 
 // ------------------------------------------------------------------------------------------------ Philox
 struct U4 { uint32_t x, y, z, w; };
@@ -159,19 +183,28 @@ __device__ __forceinline__ uint32_t sample_quantile_u32(const uint32_t* __restri
     return (uint32_t)(lo + (((hi - lo) * g) >> 8));
 }
 
-// 31-bit Bernoulli threshold ceil-ish((1 - exp(-h / 2^32)) * 2^31) of a hazard h given in units of 2^-32,
-// in integer arithmetic (oracle.hazard_threshold_fx): h = i / 256 + l with l < 2^-8,
+// 31-bit Bernoulli threshold round((1 - exp(-h)) * 2^31) of a hazard h = i / 256 + l / 2^32 (l < 2^24), in
+// 32-bit integer arithmetic (oracle.hazard_threshold_fx):
 //   1 - exp(-h) = Q[i] + u - Q[i] u,  Q[i] = 1 - exp(-i / 256) (table, 0.32 fixed point),
 //   u = 1 - exp(-l) = l - l^2/2 + l^3/6  (remainder < 2^-36).
+__device__ __forceinline__ uint32_t hazard_threshold_core(const uint32_t* __restrict__ omexp, uint32_t i, uint32_t l) {
+    const uint32_t q = __ldg(omexp + i);
+    const uint32_t l2 = (uint32_t)(((unsigned long long)l * l) >> 33);
+    const uint32_t l3 = (__umulhi(l2, l) * 171u) >> 9;          // (l^3 / 2 >> 32) / 3; the operand is < 128
+    const uint32_t u = l - l2 + l3;
+    uint32_t p = q + u - __umulhi(q, u);
+    p = p < q ? 0xFFFFFFFFu : p;                                // the sum can reach 2^32 at the end of the table
+    return (p >> 1) + (p & 1u);
+}
+// hazard in units of 2^-32
 __device__ __forceinline__ uint32_t hazard_threshold_fx(const uint32_t* __restrict__ omexp, unsigned long long h) {
     if (h >= ((unsigned long long)ABM_OMEXP_N << 24)) return 0x80000000u;     // exp(-32) < 2^-46
-    const uint32_t i = (uint32_t)(h >> 24), l = (uint32_t)h & 0xFFFFFFu;
-    const unsigned long long q = __ldg(omexp + i);
-    const unsigned long long l2 = ((unsigned long long)l * l) >> 33;
-    const unsigned long long l3 = ((l2 * l) >> 32) / 3ull;
-    const unsigned long long u = (unsigned long long)l - l2 + l3;
-    const unsigned long long p = q + u - ((q * u) >> 32);
-    return (uint32_t)((p + 1ull) >> 1);
+    return hazard_threshold_core(omexp, (uint32_t)(h >> 24), (uint32_t)h & 0xFFFFFFu);
+}
+// hazard in units of 2^-24 (household sums of the qfx table)
+__device__ __forceinline__ uint32_t hazard_threshold_q24(const uint32_t* __restrict__ omexp, uint32_t hq) {
+    const uint32_t i = hq >> 16;
+    return i >= (uint32_t)ABM_OMEXP_N ? 0x80000000u : hazard_threshold_core(omexp, i, (hq & 0xFFFFu) << 8);
 }
 
 // sub-step index at which `date < now` first holds: floor(t / step) + 1, by multiply-high with
@@ -389,14 +422,14 @@ constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
 
 template <uint32_t MODE>
 __global__ void __launch_bounds__(THREADS)
-abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const StepArgs s) {
+abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* __restrict__ clk, const uint32_t mode_rt) {
     __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
     __shared__ unsigned int s_acc[WARPS][2 * ABM_MAX_STATUS];   // per-warp home-pool pressure sums / head counts
     __shared__ int s_tally[N_TALLY];
     __shared__ int s_home[WARPS];
     __shared__ unsigned int s_done;
 
-    const uint32_t mode = MODE == RUNTIME_MODE ? s.mode : ((MODE & ~M_WEEKDAY) | (s.mode & M_WEEKDAY));
+    const uint32_t mode_static = MODE == RUNTIME_MODE ? mode_rt : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t sub = blockIdx.x * WARPS + wid;
     const unsigned long long info = __ldg(T.sub_info + sub);
@@ -410,7 +443,11 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     // household index of each slot within the sub-tile (static, one byte per slot): issued with the hot
     // words so the household phase does not wait for a dependent DRAM round trip
     uint32_t ix = 0;
-    if (mode & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
+    if (mode_static & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
+    // the clock (sub-step index, tick, weekday) is read after the hot loads are in flight
+    const StepArgs s = step_args(T, clk, mode_static);
+    const uint32_t mode = s.mode;
+    unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
 
     if (tid < N_TALLY) s_tally[tid] = 0;
     if (lane < 2 * ABM_MAX_STATUS) s_acc[wid][lane] = 0u;
@@ -443,7 +480,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             if (c3) atomicAdd(hz + i3, __ldg(q + rate_index(f3)));
             __syncwarp();
             for (int h = lane; h < n_hh; h += 32)     // one threshold per household (0 when nobody is contagious)
-                hz[h] = hazard_threshold_fx(T.omexp, (unsigned long long)hz[h] << 8);
+                hz[h] = hazard_threshold_q24(T.omexp, hz[h]);
             __syncwarp();
             constexpr uint32_t SH_VAL = EPI_S | (LOC_HOME << F_LOC_SHIFT);
             if ((f0 & CH_MASK) == SH_VAL) t0 = hz[i0];
@@ -491,7 +528,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_FUNNEL_RO(odd, {
                 uint32_t thr = 0;
                 if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
-                    thr = hazard_threshold_fx(T.omexp, Wk.hbig_read[big_slot(T, cid0 + J)] << 8);
+                    thr = hazard_threshold_fx(T.omexp, ((s.k & 1) ? Wk.hbig2[0] : Wk.hbig2[1])[big_slot(T, cid0 + J)] << 8);
                 } else {
                     const int pool = pool_of(G, fj, aj, slot0 + J, L0);
                     if (pool >= 0) thr = __ldg(Wk.thr_out + pool * A + status_of(fj));
@@ -599,7 +636,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         }
 
         // ============================================================ A(k): pressure / headcount tables
-        unsigned long long* acc_r = Wk.acc + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+        unsigned long long* acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
         unsigned long long* acc_n = acc_r + (size_t)T.P * A;
         // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
         // destinations: predicated global adds.  Schools, the hospital of district 0 (quirk Q3) and
@@ -663,7 +700,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                 if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
             } else if (cont && (fj & (LOCF | F_BIGHH)) == F_BIGHH) {
                 const uint32_t qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0) + rate_index(fj));
-                atomicAdd(Wk.hbig_write + big_slot(T, cid0 + J), (unsigned long long)qv);
+                atomicAdd(((s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0]) + big_slot(T, cid0 + J), (unsigned long long)qv);
             }
         })
     }
@@ -688,7 +725,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     if ((mode & M_DENSE_A) && lane < 2 * ABM_MAX_STATUS) {
         // lanes 0..11: pressure sums, lanes 12..23: head counts; consecutive warps of one home district are merged
         const int b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
-        unsigned long long* dst = Wk.acc + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A);
+        unsigned long long* dst = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A);
         unsigned long long sum = 0ull;
         int home = s_home[0];
         for (int w = 0; w < WARPS; ++w) {
@@ -717,22 +754,20 @@ struct TableArgs {
     int32_t do_reduce, do_threshold;
     int32_t replicas;
     int32_t write_log;
-    int32_t tick;
-    long long seeds_before_now;
 };
 
 constexpr int TABLE_THREADS = 256;
 
 __global__ void __launch_bounds__(TABLE_THREADS)
-abm_hazard_table_kernel(const DevTables T, const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ acc_next,
-                        unsigned long long* __restrict__ acc_sum, uint32_t* __restrict__ thr_out,
-                        unsigned long long* __restrict__ hbig_clear, unsigned long long* __restrict__ tally,
-                        long long* __restrict__ counters, long long* __restrict__ log_row, const TableArgs ta) {
+abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restrict__ clk, const TableArgs ta) {
     __shared__ unsigned long long s_part[TABLE_THREADS / 32][32];
     __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
+    const int k = clk->k;                               // the sub-step that was just executed
     if (L < T.P) {
+        const unsigned long long* __restrict__ acc = (k & 1) ? Wk.acc2[1] : Wk.acc2[0];
+        unsigned long long* __restrict__ acc_next = (k & 1) ? Wk.acc2[0] : Wk.acc2[1];
         // entry e < A: pressure sum of status e; A <= e < 2A: head count of status e - A
         const int e = t & 31, g = t >> 5;
         const size_t off = e < A ? (size_t)L * A + e : (size_t)n + (size_t)L * A + (e - A);
@@ -751,11 +786,11 @@ abm_hazard_table_kernel(const DevTables T, const unsigned long long* __restrict_
                 unsigned long long sum = 0ull;
 #pragma unroll
                 for (int w = 0; w < TABLE_THREADS / 32; ++w) sum += s_part[w][t];
-                acc_sum[off] = sum;
+                Wk.acc_sum[off] = sum;
                 s_row[t] = sum;
             }
         } else if (t < 2 * A) {
-            s_row[t] = acc_sum[off];
+            s_row[t] = Wk.acc_sum[off];
         }
         __syncthreads();
         if (ta.do_threshold && t < A) {
@@ -770,45 +805,70 @@ abm_hazard_table_kernel(const DevTables T, const unsigned long long* __restrict_
                                                                                : __double2ull_rz(__dmul_rn(lam, 4294967296.0));
                 thr = hazard_threshold_fx(T.omexp, h);
             }
-            thr_out[L * A + t] = thr;
+            Wk.thr_out[L * A + t] = thr;
         }
         return;
     }
     if (!ta.do_threshold) return;         // the bookkeeping below runs once per sub-step, with the thresholds
+    unsigned long long* hbig_clear = (k & 1) ? Wk.hbig2[0] : Wk.hbig2[1];
     for (int i = t; i < T.n_big; i += blockDim.x) hbig_clear[i] = 0ull;
-    if (t < N_TALLY) {                    // fold the replicas of the tallies
+    {                                     // fold the replicas of the tallies: 16 threads per replica group
+        static_assert(N_TALLY == 16 && TABLE_THREADS == 256, "tally fold layout");
+        const int e = t & 15, g = t >> 4;
         unsigned long long v = 0ull;
-        for (int r = 0; r < ta.replicas; ++r) {
-            v += tally[(size_t)r * N_TALLY + t];
-            tally[(size_t)r * N_TALLY + t] = 0ull;
-        }
+        for (int r = g; r < ta.replicas; r += 16) v += Wk.tally[(size_t)r * N_TALLY + e];
+        for (int r = g; r < ta.replicas; r += 16) Wk.tally[(size_t)r * N_TALLY + e] = 0ull;
+        s_part[g >> 1][(g & 1) * 16 + e] = v;
+    }
+    __syncthreads();
+    if (t < N_TALLY) {
+        unsigned long long v = 0ull;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) v += s_part[g >> 1][(g & 1) * 16 + t];
         s_row[t] = v;
     }
     __syncthreads();
+    const int n_rows = clk->n_log_rows;
+    long long* log_row = Wk.daylog + (size_t)(n_rows < Wk.max_log_rows ? n_rows : Wk.max_log_rows) * ABM_LOG_STRIDE;
+    const long long seeds_before = clk->seeds_before;
+    const int now = clk->now;
     if (t < 12) {
         // counters[0..7] cumulative, counters[8..11] current exposed / contagious / hospitalised / critical
-        long long v = counters[t];
+        long long v = Wk.counters[t];
         if (t < 8) {
             v += (long long)s_row[t];
-            counters[t] = v;
+            Wk.counters[t] = v;
             if (ta.write_log) {
                 const int col = t < 6 ? t : (t == 6 ? ABM_C_ASYMPTOMATIC_COUNT : ABM_C_SYMPTOMATIC_COUNT);
-                log_row[col] = v + (t == CUM_INFECTED ? ta.seeds_before_now : 0);
+                log_row[col] = v + (t == CUM_INFECTED ? seeds_before : 0);
             }
         } else {
             v += (long long)s_row[PRE_EXPOSED + (t - 8)];
             if (ta.write_log) log_row[ABM_C_CURRENT_EXPOSED_CASES + (t - 8)] = v;
             v += (long long)s_row[POST_EXPOSED + (t - 8)];
-            counters[t] = v;
+            Wk.counters[t] = v;
         }
-        if (t == 0 && ta.write_log) log_row[ABM_C_TICK] = ta.tick;
+        if (t == 0 && ta.write_log) log_row[ABM_C_TICK] = now;
+    }
+    __syncthreads();
+    if (t == 0) {                         // advance the clock (base_model.py:177-179)
+        const int minute_abs = clk->minute_abs + T.step_ticks;
+        clk->k = k + 1;
+        clk->now = now + T.step_ticks;
+        clk->minute_abs = minute_abs;
+        clk->weekday = (clk->weekday0 + minute_abs / DAY) % 7;
+        if (ta.write_log && n_rows < Wk.max_log_rows) clk->n_log_rows = n_rows + 1;
+        clk->seeds_before = seeds_before + clk->seeds_at_now;
+        clk->seeds_at_now = 0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ seeding
-__global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned long long* tally, const int64_t* slots,
-                                const int64_t* ids, int64_t n, int32_t k, int32_t now) {
+__global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned long long* tally, DevClock* clk,
+                                const int64_t* slots, const int64_t* ids, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t k = clk->k, now = clk->now;
+    if (i == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&clk->seeds_at_now), (unsigned long long)n);
     if (i < n) {
         const int64_t slot = slots[i];
         uint32_t a = G.aux[slot];

@@ -79,7 +79,8 @@ typedef struct {
     uint64_t seed;              /* Philox key                                                       */
     double symptomatic_rate;    /* params.SYMPTOMATIC_RATE                                          */
     double critical_fatality_rate;
-    void* stream;               /* cudaStream_t to enqueue on (NULL = the legacy default stream)    */
+    void* stream;               /* cudaStream_t to enqueue on (NULL = the library creates its own)  */
+    int32_t use_graph;          /* replay whole simulated days as one CUDA graph (needs a capturable stream) */
     int32_t world_size;         /* ranks sharing the district tables (1 = no collective)            */
     int32_t rank;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1            */
@@ -152,6 +153,11 @@ int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* th
 /* Bracket every main-kernel launch with CUDA events (bench roofline); totals since last reset. */
 int abm_set_profiling(abm_handle* h, int32_t on);
 int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches);
+/* Checkpoint / resume (the reference pickles the whole model, scenario_models.py:497-500): the agent
+ * vectors are the caller's buffers; these two calls carry the rest -- the clock, the 12 running counters
+ * and the number of seeded infections.  abm_get_state applies pending draws first (abm_flush). */
+int abm_get_state(abm_handle* h, int64_t* k, int64_t counters[ABM_N_COUNTERS], int64_t* seeded);
+int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTERS], int64_t seeded);
 int64_t abm_current_step(abm_handle* h);
 int64_t abm_launch_count(abm_handle* h);
 int abm_sync(abm_handle* h);

@@ -75,10 +75,10 @@ def hazard_threshold_fx(omexp, h):
     l = hh & np.uint64(0xFFFFFF)
     q = omexp[i].astype(np.uint64)
     l2 = (l * l) >> np.uint64(33)
-    l3 = ((l2 * l) >> np.uint64(32)) // np.uint64(3)
+    l3 = (((l2 * l) >> np.uint64(32)) * np.uint64(171)) >> np.uint64(9)     # == // 3 for operands < 256
     u = l - l2 + l3
-    p = q + u - ((q * u) >> np.uint64(32))
-    thr = ((p + np.uint64(1)) >> np.uint64(1)).astype(np.uint32)
+    p = np.minimum(q + u - ((q * u) >> np.uint64(32)), np.uint64(0xFFFFFFFF))
+    thr = ((p >> np.uint64(1)) + (p & np.uint64(1))).astype(np.uint32)
     return np.where(big, np.uint32(0x80000000), thr).astype(np.uint32)
 
 

@@ -149,3 +149,39 @@ def test_counters_and_district_statistics(built_library):
     assert np.array_equal(sym, want_sym)
     assert np.array_equal(dpop, np.bincount(pop.district, minlength=spec.n_districts))
     sim.close()
+
+
+def test_graph_replay_equals_plain_launches(built_library):
+    """Whole days replayed as one CUDA graph (device-resident clock) give the same trajectory as
+    sub-step-by-sub-step launches, including the day log."""
+    spec, pop, seeds, tab = small_case(n_agents=20_000, seed=17)
+    a, b = _sim(spec, pop, 6, tab, use_graph=True), _sim(spec, pop, 6, tab, use_graph=False)
+    for s in (a, b):
+        s.seed_infections(seeds)
+    a.step(6 * 21 + 2)                   # graph path for the whole days in the middle, plain launches at both ends
+    for n in (5, 6 * 20, 3):
+        b.step(n)
+    assert_state_equal(a.state(), b.state(), 'graph vs plain')
+    assert np.array_equal(a.read_log(), b.read_log())
+    assert a.launch_count == b.launch_count
+    a.close(); b.close()
+
+
+def test_checkpoint_restore_resumes_identically(built_library):
+    """checkpoint() -> fresh handle -> restore() continues exactly like the uninterrupted run
+    (the reference's pickle / unpickle of the model, scenario_models.py:497-500)."""
+    spec, pop, seeds, tab = small_case(n_agents=20_000, seed=19)
+    a = _sim(spec, pop, 11, tab)
+    a.seed_infections(seeds)
+    a.step(6 * 7 + 3)                    # stop in the middle of a day, while agents are out
+    ck = a.checkpoint()
+    b = _sim(spec, pop, 11, tab, upload=False)
+    b.restore(ck)
+    assert_state_equal(a.state(), b.state(), 'restored state')
+    a.step(6 * 6)
+    b.step(6 * 6)
+    assert_state_equal(a.state(), b.state(), 'after resuming')
+    la, lb = a.log_dicts(), b.log_dicts()
+    assert la[-len(lb):] == lb and len(lb) == 6
+    assert a.counters() == b.counters()
+    a.close(); b.close()

@@ -27,10 +27,10 @@ seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.
 sim = Simulation(spec, pop, seed=2020, tables=tables.build_tables(spec), max_days=a.days + 4)
 sim.seed_infections(seeds)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.days + 1)]
-ev[0].record()
+ev[0].record(sim.stream)
 for d in range(a.days):
     sim.step(6)
-    ev[d + 1].record()
+    ev[d + 1].record(sim.stream)
 torch.cuda.synchronize()
 ms = np.array([ev[d].elapsed_time(ev[d + 1]) for d in range(a.days)])
 log = sim.log_dicts()
