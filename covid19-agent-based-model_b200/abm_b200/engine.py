@@ -34,7 +34,7 @@ class AbmConfig(ct.Structure):
                 ('start_minute_of_day', ct.c_int32), ('start_weekday', ct.c_int32), ('mild_active', ct.c_int32),
                 ('max_log_rows', ct.c_int32), ('device', ct.c_int32), ('seed', ct.c_uint64),
                 ('symptomatic_rate', ct.c_double), ('critical_fatality_rate', ct.c_double), ('stream', ct.c_void_p),
-                ('use_graph', ct.c_int32), ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
+                ('use_graph', ct.c_int32), ('use_pdl', ct.c_int32), ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
 
 
 class AbmTables(ct.Structure):
@@ -51,7 +51,7 @@ class AbmAgentPtrs(ct.Structure):
 
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
            'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
-           'abm_kernel_time', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
+           'abm_kernel_time', 'abm_table_time', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
            'abm_version', 'abm_nccl_unique_id']
 
 _lib = None
@@ -82,6 +82,7 @@ def load_library(path=LIB_PATH):
     lib.abm_debug_tables.argtypes = [vp, vp, vp, vp]
     lib.abm_set_profiling.argtypes = [vp, ct.c_int32]
     lib.abm_kernel_time.argtypes = [vp, ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
+    lib.abm_table_time.argtypes = [vp, ct.POINTER(ct.c_double)]
     lib.abm_get_state.argtypes = [vp, ct.POINTER(ct.c_int64), vp, ct.POINTER(ct.c_int64)]
     lib.abm_set_state.argtypes = [vp, ct.c_int64, vp, ct.c_int64]
     lib.abm_current_step.argtypes = [vp]
@@ -155,7 +156,7 @@ class Simulation:
 
     def __init__(self, spec: ModelSpec, pop: Population, seed=0, device=0, tables=None, max_days=400,
                  agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None, use_graph=True,
-                 host_store=None, upload=True):
+                 host_store=None, upload=True, use_pdl=True):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('abm_b200 needs a CUDA device (no CPU fallback)')
@@ -199,6 +200,7 @@ class Simulation:
         cfg.symptomatic_rate, cfg.critical_fatality_rate = self.tab['symptomatic_rate'], self.tab['critical_fatality_rate']
         cfg.stream = self.stream.cuda_stream
         cfg.use_graph = int(bool(use_graph))
+        cfg.use_pdl = int(bool(use_pdl))
         cfg.world_size, cfg.rank = world_size, rank
         self._uid = None
         if world_size > 1:
@@ -363,6 +365,11 @@ class Simulation:
         ms, n = ct.c_double(), ct.c_int64()
         self._check(self.lib.abm_kernel_time(self.h, ct.byref(ms), ct.byref(n)))
         return ms.value, n.value
+
+    def table_time(self):
+        ms = ct.c_double()
+        self._check(self.lib.abm_table_time(self.h, ct.byref(ms)))
+        return ms.value
 
     @property
     def launch_count(self):

@@ -66,6 +66,9 @@ struct abm_handle {
     size_t prof_used = 0;
     double prof_ms = 0.0;
     int64_t prof_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_table_events;   // around the table kernel(s) of a sub-step
+    size_t prof_table_used = 0;
+    double prof_table_ms = 0.0;
     int64_t launches = 0;
     // NCCL
     void* nccl_lib = nullptr;
@@ -116,6 +119,19 @@ int alloc_zero(abm_handle* h, size_t count, Tp** dev_out) {
 
 int32_t hour_of(const abm_config& c, int64_t tick) { return (int32_t)(((c.start_minute_of_day + tick) / 60) % 24); }
 
+// Launch with the programmatic-serialization attribute: the kernel may start while its predecessor in the
+// stream is still draining (see launch_dependents / grid_dependency_wait in abm_kernels.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 DevWork make_work(const abm_handle* h) {
     DevWork w{};
     w.acc2[0] = h->acc[0]; w.acc2[1] = h->acc[1];
@@ -145,9 +161,10 @@ int launch_main(abm_handle* h, uint32_t mode) {
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
     const dim3 grid((unsigned)h->cfg.n_tiles), block(THREADS);
-    const uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
+    uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
+    const uint32_t rt_bits = (mode & M_STEP) ? 0u : M_NO_EARLY_DEPENDENTS;   // a flush is followed by a sub-step kernel, not a table kernel
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
-#define ABM_LAUNCH(MODE) abm_substep_kernel<MODE><<<grid, block, 0, h->stream>>>(h->T, h->G, w, h->clock, m)
+#define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_substep_kernel<MODE>, grid, block, h->stream, h->cfg.use_pdl != 0, h->T, h->G, w, (const DevClock*)h->clock, m | rt_bits))
     if (m == (M_INFECT | M_STEP)) ABM_LAUNCH(M_INFECT | M_STEP);                                        // night
     else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A);   // day
     else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
@@ -189,19 +206,32 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
     TableArgs ta{};
     ta.replicas = h->replicas;
     ta.write_log = p.log ? 1 : 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (h->profiling) {
+        if (h->prof_table_used == h->prof_table_events.size()) {
+            CUDA_TRY(h, cudaEventCreate(&t0));
+            CUDA_TRY(h, cudaEventCreate(&t1));
+            h->prof_table_events.emplace_back(t0, t1);
+        }
+        t0 = h->prof_table_events[h->prof_table_used].first;
+        t1 = h->prof_table_events[h->prof_table_used].second;
+        h->prof_table_used++;
+        CUDA_TRY(h, cudaEventRecord(t0, h->stream));
+    }
     if (h->comm) {
         ta.do_reduce = 1; ta.do_threshold = 0;
-        abm_hazard_table_kernel<<<c.n_pools, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools), dim3(TABLE_THREADS), h->stream, c.use_pdl != 0, h->T, w, h->clock, ta));
         ncclResult_t r = h->nccl_allreduce(h->acc_sum, h->acc_sum, (size_t)2 * pa, ncclUint64, ncclSum, h->comm, h->stream);
         if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
         ta.do_reduce = 0; ta.do_threshold = 1;
-        abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools + 1), dim3(TABLE_THREADS), h->stream, false, h->T, w, h->clock, ta));
         *launches += 3;
     } else {
         ta.do_reduce = 1; ta.do_threshold = 1;
-        abm_hazard_table_kernel<<<c.n_pools + 1, TABLE_THREADS, 0, h->stream>>>(h->T, w, h->clock, ta);
+        CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools + 1), dim3(TABLE_THREADS), h->stream, c.use_pdl != 0, h->T, w, h->clock, ta));
         *launches += 2;
     }
+    if (h->profiling) CUDA_TRY(h, cudaEventRecord(t1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return ABM_OK;
 }
@@ -260,6 +290,12 @@ int collect_profile(abm_handle* h) {
     }
     h->prof_launches += (int64_t)h->prof_used;
     h->prof_used = 0;
+    for (size_t i = 0; i < h->prof_table_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->prof_table_events[i].first, h->prof_table_events[i].second));
+        h->prof_table_ms += ms;
+    }
+    h->prof_table_used = 0;
     return ABM_OK;
 }
 
@@ -594,6 +630,7 @@ int abm_set_profiling(abm_handle* h, int32_t on) {
     h->profiling = on != 0;
     h->prof_ms = 0.0;
     h->prof_launches = 0;
+    h->prof_table_ms = 0.0;
     return ABM_OK;
 }
 
@@ -654,6 +691,14 @@ int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTER
     return ABM_OK;
 }
 
+int abm_table_time(abm_handle* h, double* total_ms) {
+    if (!h || !total_ms) return ABM_ERR_ARG;
+    int rc = collect_profile(h);
+    if (rc) return rc;
+    *total_ms = h->prof_table_ms;
+    return ABM_OK;
+}
+
 int64_t abm_current_step(abm_handle* h) { return h ? h->k : -1; }
 int64_t abm_launch_count(abm_handle* h) { return h ? h->launches : -1; }
 
@@ -663,6 +708,7 @@ void abm_destroy(abm_handle* h) {
     if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
     if (h->day_graph) cudaGraphExecDestroy(h->day_graph);
     for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto& p : h->prof_table_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (void* p : h->owned) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;

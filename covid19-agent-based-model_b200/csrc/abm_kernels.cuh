@@ -64,6 +64,9 @@ constexpr uint32_t SITE_INFECT = 0, SITE_COURSE_A = 1, SITE_COURSE_B = 2, SITE_M
 // whose infection draw is applied / whose tables are accumulated; any data is handled correctly either way
 constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32, M_DENSE_I = 64,
                    M_DENSE_A = 128;
+// run-time only: do not let the next kernel start early (set when the next kernel in the stream may be
+// another sub-step kernel, which reads the agent store in its prologue: abm_flush)
+constexpr uint32_t M_NO_EARLY_DEPENDENTS = 1u << 16;
 
 // ---- counters.  cum[]: events whose date has passed (cumulative log columns); cur deltas are split in
 // "pre" (infection phase: part of the state the day log sees) and "post" (transition phase: after it)
@@ -140,6 +143,14 @@ __device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock
     s.mode = mode | (s.weekday <= 4 ? M_WEEKDAY : 0u);       // base_model.py:309
     return s;
 }
+
+// ------------------------------------------------------------------------------------------------ launch overlap
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
+// may start once every CTA of its predecessor has executed launch_dependents (or exited); everything it
+// reads that the predecessor writes must come after grid_dependency_wait, which returns when the
+// predecessor has completed and its memory is visible.  Both are no-ops for a normally serialised launch.
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ Philox
 struct U4 { uint32_t x, y, z, w; };
@@ -429,7 +440,8 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     __shared__ int s_home[WARPS];
     __shared__ unsigned int s_done;
 
-    const uint32_t mode_static = MODE == RUNTIME_MODE ? mode_rt : MODE;
+    if (!(mode_rt & M_NO_EARLY_DEPENDENTS)) launch_dependents();   // the table kernel may become resident; it waits for this grid
+    const uint32_t mode_static = MODE == RUNTIME_MODE ? (mode_rt & 0xFFFFu) : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t sub = blockIdx.x * WARPS + wid;
     const unsigned long long info = __ldg(T.sub_info + sub);
@@ -444,10 +456,6 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     // words so the household phase does not wait for a dependent DRAM round trip
     uint32_t ix = 0;
     if (mode_static & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
-    // the clock (sub-step index, tick, weekday) is read after the hot loads are in flight
-    const StepArgs s = step_args(T, clk, mode_static);
-    const uint32_t mode = s.mode;
-    unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
 
     if (tid < N_TALLY) s_tally[tid] = 0;
     if (lane < 2 * ABM_MAX_STATUS) s_acc[wid][lane] = 0u;
@@ -462,8 +470,8 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     unsigned int* acc_w = s_acc[wid];
 
     // ================================================================ I(k-1): infection draws
-    if (mode & M_INFECT) {
-        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;      // 31-bit infection thresholds of the four agents
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;          // 31-bit infection thresholds of the four agents
+    if (mode_static & M_INFECT) {
         // ---- household term: 1 - prod(1 - 3 r_i) over contagious members present (base_model.py:156-175, 184-187)
         constexpr uint32_t CH_MASK = F_EPI_MASK | LOCF | F_BIGHH, CH_VAL = EPI_C | (LOC_HOME << F_LOC_SHIFT);
         const bool c0 = (f0 & CH_MASK) == CH_VAL, c1 = (f1 & CH_MASK) == CH_VAL, c2 = (f2 & CH_MASK) == CH_VAL,
@@ -488,6 +496,17 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             if ((f2 & CH_MASK) == SH_VAL) t2 = hz[i2];
             if ((f3 & CH_MASK) == SH_VAL) t3 = hz[i3];
         }
+    }
+
+    // Everything above depends only on the agent store, which the previous sub-step kernel finished writing
+    // before the table kernel started.  From here on the outputs of the table kernel are needed: thresholds,
+    // cleared accumulators, the advanced clock.
+    grid_dependency_wait();
+    const StepArgs s = step_args(T, clk, mode_static);
+    const uint32_t mode = s.mode;
+    unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
+
+    if (mode & M_INFECT) {
         // ---- outside pools and big households: susceptible and not (at home in a small household).
         // Home-district pool and trip destinations are one table look-up (predicated, all four agents);
         // schools, the hospital of district 0 and big households are rare and go through the funnel.
@@ -762,6 +781,8 @@ __global__ void __launch_bounds__(TABLE_THREADS)
 abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restrict__ clk, const TableArgs ta) {
     __shared__ unsigned long long s_part[TABLE_THREADS / 32][32];
     __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
+    grid_dependency_wait();       // the sub-step kernel has completed: its atomics are visible
+    launch_dependents();          // the next sub-step kernel may start its table-independent prologue
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
     const int k = clk->k;                               // the sub-step that was just executed

@@ -81,6 +81,7 @@ typedef struct {
     double critical_fatality_rate;
     void* stream;               /* cudaStream_t to enqueue on (NULL = the library creates its own)  */
     int32_t use_graph;          /* replay whole simulated days as one CUDA graph (needs a capturable stream) */
+    int32_t use_pdl;            /* programmatic dependent launch: the next kernel's prologue overlaps the table kernel */
     int32_t world_size;         /* ranks sharing the district tables (1 = no collective)            */
     int32_t rank;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1            */
@@ -153,6 +154,8 @@ int abm_debug_tables(abm_handle* h, uint64_t* rsum, uint64_t* ncnt, uint32_t* th
 /* Bracket every main-kernel launch with CUDA events (bench roofline); totals since last reset. */
 int abm_set_profiling(abm_handle* h, int32_t on);
 int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches);
+/* Same bracket around the table kernel(s) (and the all-reduce) of every sub-step. */
+int abm_table_time(abm_handle* h, double* total_ms);
 /* Checkpoint / resume (the reference pickles the whole model, scenario_models.py:497-500): the agent
  * vectors are the caller's buffers; these two calls carry the rest -- the clock, the 12 running counters
  * and the number of seeded infections.  abm_get_state applies pending draws first (abm_flush). */
