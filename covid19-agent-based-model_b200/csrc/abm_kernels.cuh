@@ -417,6 +417,27 @@ constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
             __VA_ARGS__                                                              \
         }                                                                            \
     }
+// Same, without the warp votes: a plain divergent loop (bodies without warp collectives); lanes leave as
+// soon as their own mask is empty and the warp reconverges behind the loop.
+#define ABM_LANE_LOOP(mask, ...)                                                     \
+    while (mask) {                                                                   \
+        const int J = __ffs(mask) - 1;                                               \
+        (mask) &= (mask) - 1u;                                                       \
+        const uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));        \
+        const uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));        \
+        __VA_ARGS__                                                                  \
+    }
+#define ABM_LANE_LOOP_RW(mask, ...)                                                  \
+    while (mask) {                                                                   \
+        const int J = __ffs(mask) - 1;                                               \
+        (mask) &= (mask) - 1u;                                                       \
+        uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));              \
+        uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));              \
+        __VA_ARGS__                                                                  \
+        if (J == 0) { f0 = fj; a0 = aj; } else if (J == 1) { f1 = fj; a1 = aj; }     \
+        else if (J == 2) { f2 = fj; a2 = aj; } else { f3 = fj; a3 = aj; }            \
+        dirty = true;                                                                \
+    }
 #define ABM_FUNNEL_RW(mask, ...)                                                     \
     while (__any_sync(FULL, (mask) != 0u)) {                                         \
         if (mask) {                                                                  \
@@ -531,18 +552,22 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                 ABM_OUT_THR(f3, a3, r3, t3, 8u)
 #undef ABM_OUT_THR
             } else {
-#define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
+                // night: only travellers and the few agents of quirk Q4 are in an outside pool
+                uint32_t look = 0;
+#define ABM_OUT_THR(fj, bit)                                                                         \
                 if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
-                    const uint32_t lf = (fj) & LOCF;                                                 \
-                    if (lf == IN_HOMEPOOL || lf == IN_DEST)                                          \
-                        tj = __ldg(Wk.thr_out + (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj)); \
-                    else odd |= (bit);                                                               \
+                    if ((((fj) & LOCF) - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) look |= (bit); else odd |= (bit); \
                 }
-                ABM_OUT_THR(f0, a0, t0, 1u)
-                ABM_OUT_THR(f1, a1, t1, 2u)
-                ABM_OUT_THR(f2, a2, t2, 4u)
-                ABM_OUT_THR(f3, a3, t3, 8u)
+                ABM_OUT_THR(f0, 1u)
+                ABM_OUT_THR(f1, 2u)
+                ABM_OUT_THR(f2, 4u)
+                ABM_OUT_THR(f3, 8u)
 #undef ABM_OUT_THR
+                ABM_LANE_LOOP(look, {
+                    const uint32_t pool = (fj & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0;
+                    const uint32_t thr = __ldg(Wk.thr_out + pool * A + status_of(fj));
+                    if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
+                })
             }
             ABM_FUNNEL_RO(odd, {
                 uint32_t thr = 0;
@@ -590,7 +615,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_GO_HOME(f2, 4u)
             ABM_GO_HOME(f3, 8u)
 #undef ABM_GO_HOME
-            ABM_FUNNEL_RW(away, {
+            ABM_LANE_LOOP_RW(away, {
                 if (G.t_return[slot0 + J] < s.now) {                                    // :285-293
                     aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
                     fj = fj & ~(F_AWAY | LOCF);
@@ -620,13 +645,14 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
 #undef ABM_MOVER
             // district movers at home whose OD draw falls in the stay-home interval of their row, and movers
             // that are neither away nor district movers, just go about their economic activity
-            uint32_t trav = 0;        // away agents and agents whose draw leaves the home district
+            uint32_t away = 0, leave = 0;   // movers that are away on paper / whose draw leaves the home district
             U4 XO = U4{0u, 0u, 0u, 0u};
             if (want_od) XO = group_draws(T, cid0, s.k, SITE_OD);
 #define ABM_GO_OUT(fj, xo, bit)                                                                      \
             if (mover & (bit)) {                                                                     \
                 const uint32_t u = (xo) >> 1;                                                        \
-                if (((fj) & F_AWAY) || (((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi))) trav |= (bit); \
+                if ((fj) & F_AWAY) away |= (bit);                                                    \
+                else if (((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi)) leave |= (bit);            \
                 else { const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf; } \
             }
             ABM_GO_OUT(f0, XO.x, 1u)
@@ -634,23 +660,29 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_GO_OUT(f2, XO.z, 4u)
             ABM_GO_OUT(f3, XO.w, 8u)
 #undef ABM_GO_OUT
-            ABM_FUNNEL_RW(trav, {
-                if ((fj & F_AWAY) && G.t_return[slot0 + J] < s.now) {                   // :342-360 back in the home district
+            // travellers: back in the home district when the stay is over (:342-360), then like everybody else
+            ABM_LANE_LOOP_RW(away, {
+                bool out_again = false;
+                if (G.t_return[slot0 + J] < s.now) {
                     aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
                     fj &= ~F_AWAY;
+                    const uint32_t u = word_of(XO, J) >> 1;
+                    out_again = (fj & F_DMOVER) && !(u >= od_lo && u < od_hi);
                 }
-                bool left = false;
-                if ((fj & F_DMOVER) && !(fj & F_AWAY)) {                                // :366-370
-                    const uint32_t dest = od_destination(od_row, T.D, word_of(XO, J) >> 1);
-                    if (dest != (uint32_t)L0) {                                         // :410-439
-                        const U4 XS = group_draws(T, cid0, s.k, SITE_STAY);
-                        G.t_return[slot0 + J] = stay_return_tick(T, word_of(XS, J), s.weekday, (uint32_t)L0, dest, s.now);
-                        fj = set_loc(fj, LOC_DEST) | F_AWAY;
-                        aj = (aj & 0xFFFF0000u) | dest;
-                        left = true;
-                    }
+                if (out_again) leave |= 1u << J;
+                else fj = set_loc(fj, econ_loc(fj));                                    // :331-339, :346-352
+            })
+            // district movers whose draw is not in the stay-home interval: find the destination (:366-441)
+            ABM_FUNNEL_RW(leave, {
+                const uint32_t dest = od_destination(od_row, T.D, word_of(XO, J) >> 1);
+                if (dest != (uint32_t)L0) {                                             // :410-439
+                    const U4 XS = group_draws(T, cid0, s.k, SITE_STAY);
+                    G.t_return[slot0 + J] = stay_return_tick(T, word_of(XS, J), s.weekday, (uint32_t)L0, dest, s.now);
+                    fj = set_loc(fj, LOC_DEST) | F_AWAY;
+                    aj = (aj & 0xFFFF0000u) | dest;
+                } else {
+                    fj = set_loc(fj, econ_loc(fj));
                 }
-                if (!left) fj = set_loc(fj, econ_loc(fj));                              // :331-339, :346-352
             })
         }
 
@@ -666,24 +698,26 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         if (mode & M_DENSE_A) {
             // per-lane head counts in 4-bit fields (status 0..11), widened to bytes for three warp reductions
             unsigned long long cw = 0ull;
-#define ABM_COUNT(fj, aj, bit)                                                                       \
+            uint32_t dest = 0;
+#define ABM_COUNT(fj, bit)                                                                           \
             {                                                                                        \
                 const uint32_t lf = (fj) & LOCF;                                                     \
-                const bool cont = ((fj) & F_EPI_MASK) == EPI_C;                                      \
                 if (lf == IN_HOMEPOOL) {                                                             \
                     cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);                          \
-                    if (cont) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj)));        \
-                } else if (lf == IN_DEST) {                                                          \
-                    const uint32_t e = cur_of(aj) * A + status_of(fj);                               \
-                    atomicAdd(acc_n + e, 1ull);                                                      \
-                    if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
-                } else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj))); \
+                } else if (lf == IN_DEST) dest |= (bit);                                             \
+                else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
             }
-            ABM_COUNT(f0, a0, 1u)
-            ABM_COUNT(f1, a1, 2u)
-            ABM_COUNT(f2, a2, 4u)
-            ABM_COUNT(f3, a3, 8u)
+            ABM_COUNT(f0, 1u)
+            ABM_COUNT(f1, 2u)
+            ABM_COUNT(f2, 4u)
+            ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
+            ABM_LANE_LOOP(dest, {
+                const uint32_t e = cur_of(aj) * A + status_of(fj);
+                atomicAdd(acc_n + e, 1ull);
+                if ((fj & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
+            })
             const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
             const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
             const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
@@ -695,20 +729,23 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             }
         } else {
             // night: hardly anybody is in an outside pool
-#define ABM_COUNT(fj, aj, bit)                                                                       \
+            uint32_t pooled = 0;
+#define ABM_COUNT(fj, bit)                                                                           \
             {                                                                                        \
                 const uint32_t lf = (fj) & LOCF;                                                     \
-                if (lf == IN_HOMEPOOL || lf == IN_DEST) {                                            \
-                    const uint32_t e = (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj); \
-                    atomicAdd(acc_n + e, 1ull);                                                      \
-                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
-                } else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) pooled |= (bit);                   \
+                else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
             }
-            ABM_COUNT(f0, a0, 1u)
-            ABM_COUNT(f1, a1, 2u)
-            ABM_COUNT(f2, a2, 4u)
-            ABM_COUNT(f3, a3, 8u)
+            ABM_COUNT(f0, 1u)
+            ABM_COUNT(f1, 2u)
+            ABM_COUNT(f2, 4u)
+            ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
+            ABM_LANE_LOOP(pooled, {
+                const uint32_t e = ((fj & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj);
+                atomicAdd(acc_n + e, 1ull);
+                if ((fj & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
+            })
         }
         ABM_FUNNEL_RO(work, {
             const int pool = pool_of(G, fj, aj, slot0 + J, L0);
