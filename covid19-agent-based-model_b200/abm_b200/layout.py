@@ -175,9 +175,11 @@ def update_static_fields(flags: np.ndarray, pop: Population, sm: SlotMap):
     return flags
 
 
-def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_households_before: int = 0):
+def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, household_ids=None, econ_loc=None):
     """Device arrays (numpy copies over slots) -> reference-style vectors over local agents, in the
-    representation of oracle.abm_oracle.OracleModel.state_dict (ticks; T_NEVER = datetime.max)."""
+    representation of oracle.abm_oracle.OracleModel.state_dict (ticks; T_NEVER = datetime.max).
+    `household_ids` / `econ_loc` override the location ids of the agents' households / economic-activity
+    locations (the drop-in `Country` numbers households by sorted name, base_model.py:577-581)."""
     s = sm.slot_of
     f = dev['flags'][s]
     aux = dev['aux'][s]
@@ -187,11 +189,13 @@ def unpack_state(dev: dict, pop: Population, sm: SlotMap, n_districts: int, n_ho
     sym_status = np.where((f & C.F_SYMPT) != 0, 1, np.where((f & C.F_ASYMPT) != 0, 0, -1)).astype(np.int8)
     kind = ((f >> C.F_LOC_SHIFT) & C.F_LOC_MASK).astype(np.int64)
     cur = (aux & 0xFFFF).astype(np.int64)
-    household_ids = pop.household.astype(np.int64) + D
+    if household_ids is None:
+        household_ids = pop.household.astype(np.int64) + D
     H = pop.n_households
-    econ_loc = np.where(pop.econ_kind == C.EKIND_HOUSEHOLD, household_ids, pop.district.astype(np.int64))
-    if pop.econ_pool is not None:
-        econ_loc = np.where(pop.econ_kind == C.EKIND_POOL, D + H + (pop.econ_pool.astype(np.int64) - D), econ_loc)
+    if econ_loc is None:
+        econ_loc = np.where(pop.econ_kind == C.EKIND_HOUSEHOLD, household_ids, pop.district.astype(np.int64))
+        if pop.econ_pool is not None:
+            econ_loc = np.where(pop.econ_kind == C.EKIND_POOL, D + H + (pop.econ_pool.astype(np.int64) - D), econ_loc)
 
     def loc_from(kind, cur):
         return np.select([kind == C.LOC_HOME, kind == C.LOC_HOMEPOOL, kind == C.LOC_DEST, kind == C.LOC_POOL,

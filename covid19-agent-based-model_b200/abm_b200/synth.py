@@ -157,3 +157,140 @@ def pick_seeds(pop: Population, spec: ModelSpec, infect_num=None, seed=0, cases=
         k = min(int(c / total * infect_num) + 1, cand.shape[0])
         out.append(rng.choice(cand, size=k, replace=False))
     return np.sort(np.concatenate(out)).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------- data directory
+def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=None, school_columns=False):
+    """Census-style DataFrame with the columns `Country.load_agents` reads.
+    Zero-padded household names keep the string sort of base_model.py:577-581 equal to the numeric order."""
+    import pandas as pd
+    names = np.array(district_names(n_districts))
+    rng = np.random.default_rng(seed + 5)
+    hh_names = np.char.add('h_', np.char.zfill(pop.household.astype(str), 9))
+    d_names = names[pop.district]
+    econ_loc = np.where(pop.econ_kind == C.EKIND_HOUSEHOLD, hh_names, d_names)
+    status_names = np.array(C.ECONOMIC_STATUS_NAMES if status_names is None else status_names)
+    df = pd.DataFrame({
+        'person_id': np.arange(pop.n),
+        'age': pop.age.astype(np.int64),
+        'sex': rng.choice(['f', 'm'], pop.n),
+        'household_id': hh_names,
+        'district_id': d_names,
+        'economic_status': status_names[pop.status],
+        'economic_activity_location_id': econ_loc,
+    })
+    for k, v in pop.extras.items():
+        df[k] = v
+    if school_columns:
+        # pupils get a school of ~400 in their home district and a re-opening phase 1..5 by age band
+        pupil = pop.status == list(status_names).index('In School')
+        school_no = (np.cumsum(pupil) // 400).astype(str)
+        df['school_id'] = np.where(pupil, np.char.add(np.char.add('s_', d_names), np.char.add('_', school_no)), '')
+        df['school_id_district'] = np.where(pupil, d_names, '')
+        df['phase'] = np.where(pupil, 1 + (pop.age % 5), 0)
+    return df
+
+
+def _xlsx_sheet_xml(rows):
+    def col_name(j):
+        s = ''
+        j += 1
+        while j:
+            j, r = divmod(j - 1, 26)
+            s = chr(65 + r) + s
+        return s
+
+    def cell(v, i, j):
+        ref = f'{col_name(j)}{i + 1}'
+        if isinstance(v, str):
+            return f'<c r="{ref}" t="inlineStr"><is><t>{v.replace("&", "&amp;").replace("<", "&lt;")}</t></is></c>'
+        return f'<c r="{ref}"><v>{v!r}</v></c>'
+    body = ''.join(f'<row r="{i + 1}">' + ''.join(cell(v, i, j) for j, v in enumerate(r)) + '</row>' for i, r in enumerate(rows))
+    return ('<?xml version="1.0" encoding="UTF-8" standalone="yes"?>'
+            '<worksheet xmlns="http://schemas.openxmlformats.org/spreadsheetml/2006/main"><sheetData>' + body +
+            '</sheetData></worksheet>')
+
+
+def write_interaction_workbook(path, status_names, matrix, sizes):
+    """Minimal .xlsx with the two sheets `ParamsConfig.set_interaction_parameters` reads (params.py:282-288)."""
+    import zipfile
+    matrix = np.asarray(matrix, dtype=float)
+    sheet_m = [[''] + list(status_names)] + [[n] + [float(v) for v in matrix[i]] for i, n in enumerate(status_names)]
+    sheet_s = [['', 'interactions']] + [[n, int(sizes[i])] for i, n in enumerate(status_names)]
+    ct = ('<?xml version="1.0" encoding="UTF-8" standalone="yes"?>'
+          '<Types xmlns="http://schemas.openxmlformats.org/package/2006/content-types">'
+          '<Default Extension="rels" ContentType="application/vnd.openxmlformats-package.relationships+xml"/>'
+          '<Default Extension="xml" ContentType="application/xml"/>'
+          '<Override PartName="/xl/workbook.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.sheet.main+xml"/>'
+          '<Override PartName="/xl/worksheets/sheet1.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.worksheet+xml"/>'
+          '<Override PartName="/xl/worksheets/sheet2.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.worksheet+xml"/>'
+          '</Types>')
+    rels = ('<?xml version="1.0" encoding="UTF-8" standalone="yes"?>'
+            '<Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+            '<Relationship Id="rId1" Type="http://schemas.openxmlformats.org/officeDocument/2006/relationships/officeDocument" Target="xl/workbook.xml"/>'
+            '</Relationships>')
+    wb = ('<?xml version="1.0" encoding="UTF-8" standalone="yes"?>'
+          '<workbook xmlns="http://schemas.openxmlformats.org/spreadsheetml/2006/main" '
+          'xmlns:r="http://schemas.openxmlformats.org/officeDocument/2006/relationships"><sheets>'
+          '<sheet name="interactions" sheetId="1" r:id="rId1"/><sheet name="interaction_matrix" sheetId="2" r:id="rId2"/>'
+          '</sheets></workbook>')
+    wb_rels = ('<?xml version="1.0" encoding="UTF-8" standalone="yes"?>'
+               '<Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+               '<Relationship Id="rId1" Type="http://schemas.openxmlformats.org/officeDocument/2006/relationships/worksheet" Target="worksheets/sheet1.xml"/>'
+               '<Relationship Id="rId2" Type="http://schemas.openxmlformats.org/officeDocument/2006/relationships/worksheet" Target="worksheets/sheet2.xml"/>'
+               '</Relationships>')
+    with zipfile.ZipFile(path, 'w', zipfile.ZIP_DEFLATED) as z:
+        z.writestr('[Content_Types].xml', ct)
+        z.writestr('_rels/.rels', rels)
+        z.writestr('xl/workbook.xml', wb)
+        z.writestr('xl/_rels/workbook.xml.rels', wb_rels)
+        z.writestr('xl/worksheets/sheet1.xml', _xlsx_sheet_xml(sheet_s))
+        z.writestr('xl/worksheets/sheet2.xml', _xlsx_sheet_xml(sheet_m))
+
+
+def write_data_dir(root, spec: ModelSpec, pop: Population, seed_cases=None, sample_tag=100, seed=0,
+                   lockdown_interaction_scale=0.5, school_columns=False):
+    """Synthesise the data directory `run_scenario` expects (the real inputs are private): census pickle, OD csv,
+    stay pickle, line list, intra-district mobility rates, interaction workbooks (normal / lockdown / sensitivity)
+    and the risk csv.  Point COVID19_ABM_DATA_DIR at `root` to use it.  Returns the census file name."""
+    import os
+    import pickle
+    import pandas as pd
+    D = spec.n_districts
+    names = district_names(D)
+    for sub in ('raw', 'preprocessed/census', 'preprocessed/mobility', 'preprocessed/line_list', 'preprocessed/risk', 'logs'):
+        os.makedirs(os.path.join(root, sub), exist_ok=True)
+    mob = os.path.join(root, 'preprocessed', 'mobility')
+    idx = pd.MultiIndex.from_product([range(7), names], names=['weekday', 'home_region'])
+    pd.DataFrame(spec.od_cum.reshape(7 * D, D), index=idx, columns=names).to_csv(
+        os.path.join(mob, 'daily_region_transition_probability-new-district-pre-lockdown.csv'), float_format='%.17g')
+    sidx = pd.MultiIndex.from_product([range(7), names, names], names=['weekday', 'home_region', 'region'])
+    pd.DataFrame({'avg_duration': (spec.stay_mean - 0.001).reshape(-1), 'stddev_duration': (spec.stay_std - 0.001).reshape(-1)},
+                 index=sidx).to_pickle(os.path.join(mob, 'weekday_mobility_duration_count_df-new-district.pickle'))
+    pd.DataFrame({'pctdif_distance': lockdown_rates(D, seed)}, index=names).to_csv(
+        os.path.join(mob, 'intra_district_decreased_mobility_rates.csv'))
+    if seed_cases is None:
+        seed_cases = seed_case_counts(pop, spec, seed)
+    with open(os.path.join(root, 'preprocessed', 'line_list', 'latest_line_list.pickle'), 'wb') as fl:
+        pickle.dump({names[d]: c for d, c in seed_cases.items()}, fl)
+    raw = os.path.join(root, 'raw')
+    write_interaction_workbook(os.path.join(raw, 'final_close_interaction_matrix_normal.xlsx'), spec.status_names,
+                               spec.interaction_matrix, spec.interaction_sizes)
+    # the lockdown workbook is not shipped with the reference: same mixing, fewer contacts (stated choice, SURVEY 8(d))
+    write_interaction_workbook(os.path.join(raw, 'final_close_interaction_matrix_lockdown.xlsx'), spec.status_names,
+                               spec.interaction_matrix, np.maximum(1, np.rint(spec.interaction_sizes * lockdown_interaction_scale)))
+    A = spec.n_status
+    sens = np.zeros((A, A))
+    sens[:A - 1, :A - 1] = 1.0 / (A - 1)
+    sens[A - 1, A - 1] = 1.0
+    write_interaction_workbook(os.path.join(raw, 'sensitivity_interaction_matrix.xlsx'), spec.status_names, sens, np.full(A, 11))
+    rng = np.random.default_rng(seed + 613)
+    number = np.array([int(s[2:]) for s in names])
+    hw = rng.uniform(0.2, 0.7, D)
+    severe = rng.uniform(0.05, 0.16, D)
+    pd.DataFrame({'ID_2': number, 'mean_hw_risk_pop_weighted': hw, 'severe_covid_risk': severe,
+                  'severe_covid_risk_improved_1': severe * 0.9, 'severe_covid_risk_improved_2': severe * 0.8}).to_csv(
+        os.path.join(root, 'preprocessed', 'risk', 'hw_and_severe_disease_risk.csv'), index=False)
+    census = os.path.join(root, 'preprocessed', 'census', f'zimbabwe_expanded_census_consolidated_{sample_tag}pct.pickle')
+    population_to_dataframe(pop, D, seed, spec.status_names, school_columns=school_columns).to_pickle(census)
+    return census

@@ -1,0 +1,24 @@
+"""Two ranks on two GPUs reproduce the single-rank oracle trajectory (tools/multi_gpu_check.py).
+Skipped on boxes with fewer than two GPUs; the host-side sharding logic is covered on CPU by
+tests/test_sharding_gloo.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_ranks_match_single_rank_oracle(built_library):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'tools', 'multi_gpu_check.py'), '--agents', '80000',
+           '--days', '12']
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert 'multi_gpu_check ok' in res.stdout
