@@ -333,9 +333,10 @@ class Simulation:
             out[k] = a
         return out
 
-    def state(self):
+    def state(self, household_ids=None, econ_loc=None):
         """Reference-style vectors over this rank's agents (see layout.unpack_state)."""
-        return layout.unpack_state(self.download(), self.pop, self.sm, self.spec.n_districts)
+        return layout.unpack_state(self.download(), self.pop, self.sm, self.spec.n_districts,
+                                   household_ids=household_ids, econ_loc=econ_loc)
 
     def checkpoint(self):
         """Everything needed to resume: the agent vectors (numpy, slot order), the clock, the running

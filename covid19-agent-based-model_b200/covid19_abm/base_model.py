@@ -503,11 +503,9 @@ class Country:
 
     def _read_back(self):
         """All dynamic vectors, person order, reference dtypes; cached until the next step."""
-        from abm_b200 import layout
         sim = self._sim
-        canon = layout.unpack_state(sim.download(), self._pop, sim.sm, self._spec_obj.n_districts,
-                                    household_ids=self.household_ids[self._order],
-                                    econ_loc=self.economic_activity_location_ids[self._order].astype(np.int64))
+        canon = sim.state(household_ids=self.household_ids[self._order],
+                          econ_loc=self.economic_activity_location_ids[self._order].astype(np.int64))
         cp = self._canon_of_person
         f = self._fresh
         for name in _STATE_VECTORS:

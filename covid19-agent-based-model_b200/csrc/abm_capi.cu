@@ -705,8 +705,11 @@ int64_t abm_launch_count(abm_handle* h) { return h ? h->launches : -1; }
 void abm_destroy(abm_handle* h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    // the captured day holds a reference on the communicator (its all-reduce nodes): NCCL's destroy waits
+    // until every graph that captured it is gone, so the graph must die first
+    if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
-    if (h->day_graph) cudaGraphExecDestroy(h->day_graph);
     for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : h->prof_table_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (void* p : h->owned) cudaFree(p);

@@ -1,0 +1,64 @@
+"""The drop-in `covid19_abm` package on the real CUDA engine: the reference's driver sequence (ParamsConfig ->
+scenario class -> load_agents with seeding -> step loop -> log lines -> pickle) must give, person by person, the
+state an independent oracle run produces from the same inputs and draws."""
+import os
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+import dropin_flow
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _library(built_library):
+    old = os.environ.get('COVID19_ABM_DATA_DIR')
+    yield
+    if old is None:
+        os.environ.pop('COVID19_ABM_DATA_DIR', None)
+    else:
+        os.environ['COVID19_ABM_DATA_DIR'] = old
+
+
+def test_unmitigated_with_pickle_resume(tmp_path):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'UnmitigatedScenario', days=14, n_agents=20_000, pickle_at=6 * 6 + 2)
+    assert rows[-1]['infected_count'] > 500
+    from abm_b200.engine import Simulation
+    assert isinstance(m._sim, Simulation)
+    m.close()
+
+
+@pytest.mark.parametrize('scenario', ['LockdownGreatestMobilityScenario', 'IsolateSymptomaticScenario',
+                                      'HandWashingRiskScenario', 'IsolateVulnerableScenario', 'OpenSchoolsScenario'])
+def test_scenarios_match_oracle(tmp_path, scenario):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, scenario, days=10, n_agents=20_000)
+    assert rows[-1]['infected_count'] > 200
+    m.close()
+
+
+def test_school_clock_hooks_refresh_the_device(tmp_path):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'AcceleratedGovernmentOpenSchoolsScenario', days=5,
+                                        start=datetime(2020, 9, 29, 0), n_agents=20_000, school_columns=True)
+    assert m.active_school_phases[-1] == m.max_school_phase
+    safe, unsafe = m.get_safe_and_unsafe_districts()
+    assert safe.shape[0] + unsafe.shape[0] == 60
+    m.close()
+
+
+def test_run_days_equals_single_steps(tmp_path):
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    dropin_flow.build_world(root, n_agents=20_000)
+    a = dropin_flow.make_model('UnmitigatedScenario', datetime(2020, 9, 1, 0), log_file=str(tmp_path / 'a.log'))
+    b = dropin_flow.make_model('UnmitigatedScenario', datetime(2020, 9, 1, 0), log_file=str(tmp_path / 'b.log'))
+    a.run_days(9)
+    for _ in range(6 * 9):
+        b.step()
+    assert np.array_equal(a.epidemic_state, b.epidemic_state)
+    assert np.array_equal(a.current_location_ids, b.current_location_ids)
+    assert np.array_equal(a.event_ticks('date_recovered'), b.event_ticks('date_recovered'))
+    assert [r for r in dropin_flow.read_log(str(tmp_path / 'a.log'))] == [r for r in dropin_flow.read_log(str(tmp_path / 'b.log'))]
+    assert a.scheduler.real_time == b.scheduler.real_time
+    a.close(); b.close()

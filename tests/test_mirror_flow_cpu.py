@@ -1,0 +1,47 @@
+"""Host logic of the drop-in `Country` end to end on CPU, with the engine replaced by the oracle-backed test double
+(tests/fake_sim.py): person/canonical permutation, seeding, read-back properties, daily log lines, scenario clock
+hooks -> refresh, pickling and resuming.  The same flows run against the real CUDA engine in test_gpu_dropin.py."""
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+import dropin_flow
+from fake_sim import FakeSimulation
+
+
+@pytest.fixture()
+def fake_engine(monkeypatch):
+    from abm_b200 import engine
+    monkeypatch.setattr(engine, 'Simulation', FakeSimulation)
+    FakeSimulation.instances.clear()
+    yield FakeSimulation
+
+
+def test_unmitigated_flow_with_pickle_resume(tmp_path, fake_engine):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'UnmitigatedScenario', days=8, n_agents=6000, pickle_at=6 * 4 + 3)
+    assert rows[-1]['infected_count'] > 150
+    assert m.epidemic_state.dtype == np.float64
+    assert m.scheduler.real_time == datetime(2020, 9, 9, 0) and m.scheduler.steps == 48
+
+
+def test_lockdown_flow(tmp_path, fake_engine):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'LockdownGreatestMobilityScenario', days=5, n_agents=6000)
+    assert m.params.lockdown and not m.lockdown                     # quirk Q1
+
+
+def test_school_scenario_clock_hooks_refresh_the_device(tmp_path, fake_engine):
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'AcceleratedGovernmentOpenSchoolsScenario', days=4,
+                                        start=datetime(2020, 9, 29, 0), n_agents=6000, school_columns=True)
+    assert fake_engine.instances[-1].n_refresh >= 1
+    assert m.active_school_phases[-1] == m.max_school_phase        # one phase per sub-step of the 1st (quirk Q10)
+    assert (m.economic_activity_location_ids >= max(m.params.HOUSEHOLD_ID_TO_NAME) + 1).sum() > 100
+
+
+def test_real_time_cannot_be_set_while_running(tmp_path, fake_engine):
+    m, _, _ = dropin_flow.run_flow(tmp_path, 'UnmitigatedScenario', days=1, n_agents=3000)
+    with pytest.raises(RuntimeError):
+        m.scheduler.real_time = datetime(2021, 1, 1)
+    groups = m.get_location_person_ids()
+    assert sum(len(v) for v in groups.values()) == m.person_ids.shape[0]
+    assert m.scheduler.get_active_ids().shape[0] > 0

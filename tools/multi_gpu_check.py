@@ -84,14 +84,24 @@ def main():
         dist.all_reduce(flag)
     print(f'rank {rank}/{world}: agents [{lo}, {hi}) infected {int((want["epidemic_state"][lo:hi] > 0).sum())} '
           f'mismatches {bad}', flush=True)
-    sim.close()
-    if world > 1:
-        dist.destroy_process_group()
-    if int(flag.item()) != 0:
-        sys.exit(1)
-    if rank == 0:
+    failed = int(flag.item()) != 0
+    if rank == 0 and not failed:
         print(f'multi_gpu_check ok: world {world}, {a.agents} agents, {a.days} days, '
               f'infected_count {ora.log_rows[-1]["infected_count"]}', flush=True)
+
+    import threading
+
+    def teardown():
+        sim.close()
+        if world > 1:
+            dist.destroy_process_group()
+    t = threading.Thread(target=teardown, daemon=True)
+    t.start()
+    t.join(timeout=30)
+    if t.is_alive():
+        print(f'rank {rank}: tear-down stuck, exiting anyway', flush=True)
+    sys.stdout.flush()
+    os._exit(1 if failed else 0)
 
 
 if __name__ == '__main__':
