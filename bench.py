@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--cpu-agents', type=int, default=1_500_000, help='agents of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--full-run-days', type=int, default=365, help='also time a whole run of this many days from the seeding (0 = skip)')
     return ap.parse_args()
 
 
@@ -184,7 +185,7 @@ def run_cuda_arm(a):
 
     from abm_b200.engine import HostStore
     store = HostStore(spec, pop, agent_id_base=base)         # ingestion (slot map, bit packing, page-locking): untimed
-    max_days = a.spinup + a.warmup + a.steps + 16
+    max_days = max(a.spinup + a.warmup + 2 * a.steps + 16, a.full_run_days + 8)
 
     def make_sim(upload=True):
         uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None   # one id per communicator
@@ -264,10 +265,10 @@ def run_cuda_arm(a):
         del sim
         pinned = {name: torch.from_numpy(arr).pin_memory() for name, arr in ckpt['arrays'].items()}
         host_ckpt = dict(arrays=pinned, k=ckpt['k'], counters=ckpt['counters'], seeded=ckpt['seeded'])
+        sim = make_sim(upload=False)          # handle, empty device buffers, constant tables, communicator: set-up, untimed
         torch.cuda.synchronize(device)
         barrier()
         t0 = time.perf_counter()
-        sim = make_sim(upload=False)          # handle, device buffers, constant tables
         sim.restore(host_ckpt)                # host -> device copy of every per-agent vector
         h2d = sum(v.numel() * v.element_size() for v in pinned.values())
         d2h = 0
@@ -286,8 +287,31 @@ def run_cuda_arm(a):
         e2e = dict(value=n_total * a.steps / wall, unit=UNIT, h2d_bytes_per_step=h2d / a.steps,
                    d2h_bytes_per_step=d2h / a.steps, seconds=wall,
                    note='K more days from the state the timed region ended in, through Simulation (C ABI) with the agent store in '
-                        'page-locked host memory: handle creation, table upload, host->device copy of all per-agent '
-                        'vectors, K days with a log read-back per day, device->host copy of the final state word')
+                        'page-locked host memory: host->device copy of all per-agent vectors, K days with a log read-back '
+                        '(device->host, synchronising) per day, device->host copy of the final state word; handle / '
+                        'communicator creation is set-up and not timed')
+
+    # ---- the whole scenario of BASELINE.json configs[1]: 365 simulated days from the seeding, device resident
+    full_run = None
+    if a.full_run_days > 0:
+        sim.close()
+        del sim
+        sim = make_sim()
+        sim.seed_infections(synth.pick_seeds(pop, spec, infect_num=max(1, int(0.00015 * pop.n)), seed=POP_SEED + rank) + base)
+        sim.step(SUBSTEPS_PER_DAY)            # first day: plain launches + graph capture, untimed
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(sim.stream)
+        sim.step((a.full_run_days - 1) * SUBSTEPS_PER_DAY)
+        f1.record(sim.stream)
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(tf, op=torch.distributed.ReduceOp.MAX)
+        fc = sim.counters()
+        full_run = dict(days=a.full_run_days - 1, seconds=float(tf.item()) / 1e3,
+                        agent_days_per_sec=n_total * (a.full_run_days - 1) / (float(tf.item()) / 1e3),
+                        seed_fraction=0.00015, infected_at_end_this_rank=fc['infected_count'], died_at_end_this_rank=fc['died_count'])
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -305,7 +329,10 @@ def run_cuda_arm(a):
                         l2=f'per-GPU agent store {store.nbytes / 1e6:.0f} MB > 126 MB L2; the 8 B/agent hot record swept '
                            f'every sub-step is {hot_mb:.0f} MB (no explicit flush: re-sweeping it is the workload)',
                         state_at_timing={k: prevalence[k] for k in ('current_exposed_cases', 'current_contagious_cases',
-                                                                    'infected_count', 'recovered_count')}),
+                                                                    'infected_count', 'recovered_count')},
+                        timing_regime='the K timed days start after the spin-up, around the epidemic peak: the most expensive '
+                                      'days of the run; full_run is the same population over the whole scenario',
+                        full_run=full_run),
             roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks.summary())
         print(json.dumps(line), flush=True)
     _teardown(sim, world)

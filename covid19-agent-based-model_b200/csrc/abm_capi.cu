@@ -39,6 +39,8 @@ struct abm_handle {
     std::vector<void*> owned;           // device allocations to free
     unsigned long long* acc[2] = {nullptr, nullptr};   // [replicas][2][P][A] each; sub-step k accumulates into acc[k & 1]
     unsigned long long* acc_sum = nullptr;             // [2][P][A] replicas (and ranks) summed: tables of the last sub-step
+    unsigned long long* acc_local = nullptr;           // [2][P][A] this rank's replicas summed, kept across incremental sub-steps
+    bool tables_valid = false;                         // acc_local / hbig hold the sums of sub-step k - 1
     int32_t replicas = 1;
     uint32_t* thr_out = nullptr;        // [P][A]
     unsigned long long* hbig[2] = {nullptr, nullptr};
@@ -139,6 +141,7 @@ DevWork make_work(const abm_handle* h) {
     w.hbig2[0] = h->hbig[0]; w.hbig2[1] = h->hbig[1];
     w.tally = h->tally;
     w.acc_sum = h->acc_sum;
+    w.acc_local = h->acc_local;
     w.counters = h->counters;
     w.daylog = h->daylog;
     w.rep_mask = (uint32_t)h->replicas - 1u;
@@ -165,8 +168,8 @@ int launch_main(abm_handle* h, uint32_t mode) {
     const uint32_t rt_bits = (mode & M_STEP) ? 0u : M_NO_EARLY_DEPENDENTS;   // a flush is followed by a sub-step kernel, not a table kernel
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
 #define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_substep_kernel<MODE>, grid, block, h->stream, h->cfg.use_pdl != 0, h->T, h->G, w, (const DevClock*)h->clock, m | rt_bits))
-    if (m == (M_INFECT | M_STEP)) ABM_LAUNCH(M_INFECT | M_STEP);                                        // night
-    else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A);   // day
+    if (m == (M_INFECT | M_STEP | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_INCR);                       // night
+    else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR);   // day
     else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
     else if (m == (M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I);
     else if (m == M_INFECT) ABM_LAUNCH(M_INFECT);                                                       // abm_flush
@@ -180,7 +183,7 @@ int launch_main(abm_handle* h, uint32_t mode) {
 // What the next sub-step does, from the host mirror of the clock (EpidemicScheduler.step, base_model.py:33-58).
 struct SubstepPlan { uint32_t mode; bool log; };
 
-SubstepPlan plan_substep(const abm_config& c, int64_t k, bool pending_infect, bool& daytime) {
+SubstepPlan plan_substep(const abm_config& c, int64_t k, bool pending_infect, bool& daytime, bool tables_valid) {
     const int64_t tick = k * c.step_ticks;
     const int32_t hour = hour_of(c, tick);
     SubstepPlan p{};
@@ -189,6 +192,8 @@ SubstepPlan plan_substep(const abm_config& c, int64_t k, bool pending_infect, bo
     if (hour == 8) { p.mode |= M_GO_OUT; daytime = true; }        // params.py:131,135
     if (hour == 16) { p.mode |= M_GO_HOME; daytime = false; }     // params.py:132,136
     if (daytime) p.mode |= M_DENSE_A;
+    // nobody moves outside the two movement hours: the tables of the previous sub-step are updated by deltas
+    if (tables_valid && hour != 8 && hour != 16) p.mode |= M_INCR;
     p.log = hour == 8;                                            // base_model.py:1083
     if (p.log) p.mode |= M_LOG;
     return p;
@@ -206,6 +211,7 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
     TableArgs ta{};
     ta.replicas = h->replicas;
     ta.write_log = p.log ? 1 : 0;
+    ta.incremental = (p.mode & M_INCR) ? 1 : 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->profiling) {
         if (h->prof_table_used == h->prof_table_events.size()) {
@@ -259,7 +265,7 @@ int build_day_graph(abm_handle* h) {
     const bool was_profiling = h->profiling;
     h->profiling = false;
     for (int i = 0; i < spd && rc == ABM_OK; ++i) {
-        const SubstepPlan p = plan_substep(c, h->k + i, true, daytime);
+        const SubstepPlan p = plan_substep(c, h->k + i, true, daytime, true);
         logs += p.log ? 1 : 0;
         rc = enqueue_substep(h, p, &launches);
     }
@@ -351,6 +357,7 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[0]))) return rc;
     if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[1]))) return rc;
     if ((rc = alloc_zero(h, 2 * pa, &h->acc_sum))) return rc;
+    if ((rc = alloc_zero(h, 2 * pa, &h->acc_local))) return rc;
     if ((rc = alloc_zero(h, pa, &h->thr_out))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[0]))) return rc;
     if ((rc = alloc_zero(h, (size_t)cfg->n_big_households + 1, &h->hbig[1]))) return rc;
@@ -443,6 +450,7 @@ int abm_bind_agents(abm_handle* h, const abm_agent_ptrs* dev) {
 
 int abm_refresh(abm_handle* h, const uint32_t* move_thr, int32_t n_move_classes) {
     if (!h) return ABM_ERR_ARG;
+    h->tables_valid = false;             // the caller may have rewritten the agent store: recount at the next sub-step
     if (move_thr) {
         if (n_move_classes < 1) return fail(h, ABM_ERR_ARG, "n_move_classes < 1");
         const uint32_t* mt = nullptr;
@@ -490,7 +498,7 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
     int32_t left = n_substeps;
     while (left > 0) {
         // whole simulated days in the periodic regime replay the captured graph
-        if (periodic && c.use_graph && !h->graph_failed && !h->profiling && h->pending_infect && left >= spd && h->k >= spd) {
+        if (periodic && c.use_graph && !h->graph_failed && !h->profiling && h->pending_infect && h->tables_valid && left >= spd && h->k >= spd) {
             if (!h->day_graph) {
                 int rc = build_day_graph(h);
                 if (rc) return rc;
@@ -501,7 +509,7 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
                 if (rc) return rc;
                 CUDA_TRY(h, cudaGraphLaunch(h->day_graph, h->stream));
                 bool daytime = h->daytime;
-                for (int i = 0; i < spd; ++i) plan_substep(c, h->k + i, true, daytime);
+                for (int i = 0; i < spd; ++i) plan_substep(c, h->k + i, true, daytime, true);
                 h->daytime = daytime;
                 h->k += spd;
                 h->n_log_rows += h->graph_logs;
@@ -511,11 +519,12 @@ int abm_step(abm_handle* h, int32_t n_substeps) {
             }
         }
         bool daytime = h->daytime;
-        const SubstepPlan p = plan_substep(c, h->k, h->pending_infect, daytime);
+        const SubstepPlan p = plan_substep(c, h->k, h->pending_infect, daytime, h->tables_valid);
         int rc = check_limits(h, h->k + 1, h->n_log_rows + (p.log ? 1 : 0));
         if (rc) return rc;
         rc = enqueue_substep(h, p, &h->launches);
         if (rc) return rc;
+        h->tables_valid = true;
         h->daytime = daytime;
         if (p.log) h->n_log_rows++;
         h->k++;
@@ -679,6 +688,7 @@ int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTER
     h->k = k;
     h->n_log_rows = 0;
     h->pending_infect = false;
+    h->tables_valid = false;
     h->seeds.clear();
     if (seeded) h->seeds.push_back(SeedEvent{-1, seeded});
     // who is out and about follows from the hour: go_out at 8, go_home at 16 (params.py:131-136)

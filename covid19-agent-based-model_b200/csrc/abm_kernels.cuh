@@ -64,6 +64,11 @@ constexpr uint32_t SITE_INFECT = 0, SITE_COURSE_A = 1, SITE_COURSE_B = 2, SITE_M
 // whose infection draw is applied / whose tables are accumulated; any data is handled correctly either way
 constexpr uint32_t M_INFECT = 1, M_STEP = 2, M_GO_OUT = 4, M_GO_HOME = 8, M_LOG = 16, M_WEEKDAY = 32, M_DENSE_I = 64,
                    M_DENSE_A = 128;
+// INCR: nobody moves in this sub-step, so the district x status tables (and the big-household hazards) are those of
+// the previous sub-step plus the changes made by the few transitions that fire: the A(k) sweep is skipped, the
+// transitions emit signed deltas, and the table kernel adds them to the sums it kept.  All sums are integers modulo
+// 2^64, so the result is identical to a full recount.
+constexpr uint32_t M_INCR = 256;
 // run-time only: do not let the next kernel start early (set when the next kernel in the stream may be
 // another sub-step kernel, which reads the agent store in its prologue: abm_flush)
 constexpr uint32_t M_NO_EARLY_DEPENDENTS = 1u << 16;
@@ -108,6 +113,7 @@ struct DevWork {
     unsigned long long* hbig2[2];   // [n_big] household hazard of big households: written at k into hbig2[k & 1], read from the other
     unsigned long long* tally;      // [replicas][N_TALLY]
     unsigned long long* acc_sum;    // [2][P][A] replicas (and ranks) summed: tables of the last sub-step
+    unsigned long long* acc_local;  // [2][P][A] replicas of THIS rank summed (kept across incremental sub-steps)
     long long* counters;            // [12] running cumulative (0..7) and current (8..11) counters
     long long* daylog;              // [max_log_rows + 1][ABM_LOG_STRIDE]
     uint32_t rep_mask;
@@ -323,8 +329,23 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
 // update_agent_states (base_model.py:226-272) + contagious promotion (base_model.py:54-58) for one agent
 // whose next-event index is due.  Cumulative date counters are tallied the first time a date is passed;
 // the "current" counters of the day log move by the change of epidemic / clinical state.
+// What an agent contributes to the accumulated tables: used to emit the difference a transition makes.
+struct Contribution { int pool; bool cont; bool big_home; };
+__device__ __forceinline__ Contribution contribution_of(const DevAgents& G, uint32_t f, uint32_t a, uint32_t slot, int L0) {
+    Contribution c;
+    c.pool = pool_of(G, f, a, slot, L0);
+    c.cont = (f & F_EPI_MASK) == EPI_C;
+    c.big_home = c.cont && (f & (LOCF | F_BIGHH)) == F_BIGHH;
+    return c;
+}
+
+struct DeltaSink {          // where incremental sub-steps send their table changes (nullptr = full recount follows)
+    unsigned long long* acc_r; unsigned long long* acc_n; unsigned long long* hbig; int L0; int64_t cid;
+};
+
 __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
-                                                     int32_t now, int* s_tally) {
+                                                     int32_t now, int* s_tally, const DeltaSink* sink = nullptr) {
+    const uint32_t f_before = f;
     const int32_t t_c = G.t_contagious[slot], t_o = G.t_onset[slot], t_r = G.t_recovered[slot];
     const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
     const int32_t t_cs = (f & F_OUT_C) ? t_o + 13 * DAY : T_NEVER;  // hospital end = critical start (base_model.py:953)
@@ -358,6 +379,23 @@ __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const D
         if (clin == 2) atomicAdd(s_tally + POST_CRITICAL, 1);
     }
     f = (f & ~(F_EPI_MASK | CLINF | LOCF)) | epi | (clin << F_CLIN_SHIFT) | (loc << F_LOC_SHIFT);
+    if (sink && ((f ^ f_before) & (F_EPI_MASK | LOCF))) {
+        const Contribution c0 = contribution_of(G, f_before, a, slot, sink->L0), c1 = contribution_of(G, f, a, slot, sink->L0);
+        const uint32_t st = (f >> F_STATUS_SHIFT) & F_STATUS_MASK;
+        const unsigned long long rate = __ldg(T.rfx + __byte_perm(f, 0u, 0x4442u));
+        if (c0.pool != c1.pool) {
+            if (c0.pool >= 0) atomicAdd(sink->acc_n + c0.pool * T.A + st, ~0ull);           // - 1
+            if (c1.pool >= 0) atomicAdd(sink->acc_n + c1.pool * T.A + st, 1ull);
+        }
+        if (c0.pool != c1.pool || c0.cont != c1.cont) {
+            if (c0.pool >= 0 && c0.cont) atomicAdd(sink->acc_r + c0.pool * T.A + st, 0ull - rate);
+            if (c1.pool >= 0 && c1.cont) atomicAdd(sink->acc_r + c1.pool * T.A + st, rate);
+        }
+        if (c0.big_home != c1.big_home) {
+            const unsigned long long qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)sink->L0 * 256 : 0) + __byte_perm(f, 0u, 0x4442u));
+            atomicAdd(sink->hbig + big_slot(T, sink->cid), c1.big_home ? qv : 0ull - qv);
+        }
+    }
     // next event = smallest date not yet passed (fire_index is monotone, so one evaluation suffices)
     int32_t nxt = T_NEVER;
     const int32_t ts[6] = {t_c, t_o, t_h, t_cs, t_d, t_r};
@@ -599,7 +637,16 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         {
             const uint32_t lim = ((uint32_t)s.k << 16) | 0xFFFFu;      // fire index (high half of aux) <= k
             uint32_t due = (a0 <= lim ? 1u : 0u) | (a1 <= lim ? 2u : 0u) | (a2 <= lim ? 4u : 0u) | (a3 <= lim ? 8u : 0u);
-            ABM_FUNNEL_RW(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
+            if (mode & M_INCR) {
+                DeltaSink sink;
+                sink.acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+                sink.acc_n = sink.acc_r + (size_t)T.P * A;
+                sink.hbig = (s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
+                sink.L0 = L0;
+                ABM_FUNNEL_RW(due, { sink.cid = cid0 + J; fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally, &sink); })
+            } else {
+                ABM_FUNNEL_RW(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
+            }
         }
 
         // ============================================================ M(k): movement (base_model.py:274-441)
@@ -687,6 +734,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         }
 
         // ============================================================ A(k): pressure / headcount tables
+        if (!(mode & M_INCR)) {
         unsigned long long* acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
         unsigned long long* acc_n = acc_r + (size_t)T.P * A;
         // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
@@ -759,6 +807,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                 atomicAdd(((s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0]) + big_slot(T, cid0 + J), (unsigned long long)qv);
             }
         })
+        }   // full recount
     }
 
     // ================================================================ write back what changed
@@ -778,7 +827,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         const int v = s_tally[lane];
         if (v) atomicAdd(Wk.tally + (size_t)(blockIdx.x & Wk.rep_mask) * N_TALLY + lane, (unsigned long long)(long long)v);
     }
-    if ((mode & M_DENSE_A) && lane < 2 * ABM_MAX_STATUS) {
+    if ((mode & M_DENSE_A) && !(mode & M_INCR) && lane < 2 * ABM_MAX_STATUS) {
         // lanes 0..11: pressure sums, lanes 12..23: head counts; consecutive warps of one home district are merged
         const int b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
         unsigned long long* dst = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A);
@@ -810,6 +859,7 @@ struct TableArgs {
     int32_t do_reduce, do_threshold;
     int32_t replicas;
     int32_t write_log;
+    int32_t incremental;      // the sub-step just executed emitted deltas (M_INCR): add them to the kept sums
 };
 
 constexpr int TABLE_THREADS = 256;
@@ -841,9 +891,10 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             s_part[g][e] = v;
             __syncthreads();
             if (t < 2 * A) {
-                unsigned long long sum = 0ull;
+                unsigned long long sum = ta.incremental ? Wk.acc_local[off] : 0ull;
 #pragma unroll
                 for (int w = 0; w < TABLE_THREADS / 32; ++w) sum += s_part[w][t];
+                Wk.acc_local[off] = sum;
                 Wk.acc_sum[off] = sum;
                 s_row[t] = sum;
             }
@@ -869,7 +920,11 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
     }
     if (!ta.do_threshold) return;         // the bookkeeping below runs once per sub-step, with the thresholds
     unsigned long long* hbig_clear = (k & 1) ? Wk.hbig2[0] : Wk.hbig2[1];
-    for (int i = t; i < T.n_big; i += blockDim.x) hbig_clear[i] = 0ull;
+    unsigned long long* hbig_cur = (k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
+    for (int i = t; i < T.n_big; i += blockDim.x) {
+        if (ta.incremental) hbig_cur[i] += hbig_clear[i];       // deltas of this sub-step + the sums of the previous one
+        hbig_clear[i] = 0ull;
+    }
     {                                     // fold the replicas of the tallies: 16 threads per replica group
         static_assert(N_TALLY == 16 && TABLE_THREADS == 256, "tally fold layout");
         const int e = t & 15, g = t >> 4;
