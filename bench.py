@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument('--cpu-agents', type=int, default=1_500_000, help='agents of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
+                    help='N > 1: sum the tables over ranks inside the table kernel through peer memory, or with ncclAllReduce')
     ap.add_argument('--full-run-days', type=int, default=365, help='also time a whole run of this many days from the seeding (0 = skip)')
     return ap.parse_args()
 
@@ -188,10 +190,12 @@ def run_cuda_arm(a):
     max_days = max(a.spinup + a.warmup + 2 * a.steps + 16, a.full_run_days + 8)
 
     def make_sim(upload=True):
-        uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None   # one id per communicator
+        uid = None
+        if world > 1 and a.exchange == 'nccl':
+            uid = distributed.exchange_unique_id(lib, rank, world, device)       # one id per communicator
         return Simulation(spec, pop, seed=POP_SEED, device=local, tables=tab, max_days=max_days, agent_id_base=base,
                           district_start=dstart, world_size=world, rank=rank, nccl_unique_id=uid, host_store=store,
-                          upload=upload)
+                          upload=upload, exchange=a.exchange if world > 1 else None)
 
     def barrier():
         if world > 1:
@@ -324,7 +328,10 @@ def run_cuda_arm(a):
             higher_is_better=True, scaling='weak', vs_baseline=None, dtype='u32/int64', data='synthetic',
             config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.agents_per_gpu} agents per GPU x {world} GPU(s), '
                                  f'{a.districts} districts, unmitigated R0=1.9, 4 h sub-steps (6 per simulated day), '
-                                 f'household-aligned shards, NCCL all-reduce of the district x status tables per sub-step',
+                                 f'household-aligned shards' + ('' if world == 1 else (
+                                     ', district x status tables summed over ranks inside the table kernel through peer '
+                                     'memory (NVLink)' if a.exchange == 'p2p' else ', ncclAllReduce of the district x status '
+                                     'tables per sub-step')),
                         agents_total=n_total, spinup_days=a.spinup, seed_fraction=a.seed_fraction,
                         l2=f'per-GPU agent store {store.nbytes / 1e6:.0f} MB > 126 MB L2; the 8 B/agent hot record swept '
                            f'every sub-step is {hot_mb:.0f} MB (no explicit flush: re-sweeping it is the workload)',

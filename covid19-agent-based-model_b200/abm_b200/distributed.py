@@ -46,3 +46,17 @@ def sum_over_ranks(rows: np.ndarray, device):
     t = torch.from_numpy(np.ascontiguousarray(rows)).to(device)
     dist.all_reduce(t)
     return t.cpu().numpy()
+
+
+def all_gather_bytes(payload: bytes, device):
+    """Every rank's `payload` (same length everywhere), in rank order, over the existing process group."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError('torch.distributed is not initialised: the peer exchange needs it to trade buffer handles')
+    world = dist.get_world_size()
+    dev = device if dist.get_backend() == 'nccl' else 'cpu'
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().tolist()) for t in out]

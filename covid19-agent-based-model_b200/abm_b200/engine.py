@@ -18,7 +18,7 @@ from . import layout, tables as tables_mod
 from .spec import ModelSpec, Population
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libabm_b200.so')
+LIB_PATH = os.environ.get('ABM_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'libabm_b200.so')
 
 COUNTER_NAMES = ['current_contagious_count', 'infected_count', 'hospitalized_count', 'critical_count', 'died_count',
                  'recovered_count', 'current_exposed_cases', 'current_contagious_cases', 'current_hospitalized_cases',
@@ -34,7 +34,8 @@ class AbmConfig(ct.Structure):
                 ('start_minute_of_day', ct.c_int32), ('start_weekday', ct.c_int32), ('mild_active', ct.c_int32),
                 ('max_log_rows', ct.c_int32), ('device', ct.c_int32), ('seed', ct.c_uint64),
                 ('symptomatic_rate', ct.c_double), ('critical_fatality_rate', ct.c_double), ('stream', ct.c_void_p),
-                ('use_graph', ct.c_int32), ('use_pdl', ct.c_int32), ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p)]
+                ('use_graph', ct.c_int32), ('use_pdl', ct.c_int32), ('world_size', ct.c_int32), ('rank', ct.c_int32), ('nccl_unique_id', ct.c_void_p),
+                ('exchange', ct.c_int32), ('reserved', ct.c_int32)]
 
 
 class AbmTables(ct.Structure):
@@ -52,7 +53,7 @@ class AbmAgentPtrs(ct.Structure):
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
            'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
            'abm_kernel_time', 'abm_table_time', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
-           'abm_version', 'abm_nccl_unique_id']
+           'abm_version', 'abm_nccl_unique_id', 'abm_peer_export', 'abm_peer_attach', 'abm_peer_detach']
 
 _lib = None
 
@@ -95,6 +96,9 @@ def load_library(path=LIB_PATH):
     lib.abm_destroy.argtypes = [vp]
     lib.abm_destroy.restype = None
     lib.abm_nccl_unique_id.argtypes = [vp]
+    lib.abm_peer_export.argtypes = [vp, vp]
+    lib.abm_peer_attach.argtypes = [vp, vp, ct.c_int32]
+    lib.abm_peer_detach.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -156,7 +160,10 @@ class Simulation:
 
     def __init__(self, spec: ModelSpec, pop: Population, seed=0, device=0, tables=None, max_days=400,
                  agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None, use_graph=True,
-                 host_store=None, upload=True, use_pdl=True):
+                 host_store=None, upload=True, use_pdl=True, exchange=None):
+        """exchange (world_size > 1): 'p2p' sums the district x status tables over ranks inside the table kernel through
+        peer memory (one node; needs an initialised torch.distributed group to trade the buffer handles), 'nccl' uses
+        ncclAllReduce (needs `nccl_unique_id`).  Default: 'p2p' unless a unique id is given."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('abm_b200 needs a CUDA device (no CPU fallback)')
@@ -203,12 +210,25 @@ class Simulation:
         cfg.use_pdl = int(bool(use_pdl))
         cfg.world_size, cfg.rank = world_size, rank
         self._uid = None
-        if world_size > 1:
+        if exchange is None:
+            exchange = 'nccl' if nccl_unique_id is not None else 'p2p'
+        if exchange not in ('p2p', 'nccl'):
+            raise ValueError(f'unknown exchange {exchange!r}')
+        self.exchange = exchange if world_size > 1 else None
+        if world_size > 1 and exchange == 'nccl':
             self._uid = (ct.c_char * 128).from_buffer_copy(bytes(nccl_unique_id))
             cfg.nccl_unique_id = ct.cast(self._uid, ct.c_void_p)
+        cfg.exchange = 1 if (world_size > 1 and exchange == 'p2p') else 0
         self.h = ct.c_void_p()
         self._check(self.lib.abm_create(ct.byref(cfg), ct.byref(self.h)))
         self.cfg = cfg
+        if cfg.exchange == 1:
+            from . import distributed
+            mine = (ct.c_char * 64)()
+            self._check(self.lib.abm_peer_export(self.h, ct.cast(mine, ct.c_void_p)))
+            handles = distributed.all_gather_bytes(bytes(mine), self.device)
+            self._peer_handles = (ct.c_char * (64 * world_size)).from_buffer_copy(b''.join(handles))
+            self._check(self.lib.abm_peer_attach(self.h, ct.cast(self._peer_handles, ct.c_void_p), world_size))
 
         t = self.tab
         keep = dict(
@@ -378,6 +398,15 @@ class Simulation:
 
     def close(self):
         if getattr(self, 'h', None):
+            if getattr(self, 'exchange', None) == 'p2p':
+                # peers read this rank's exchange buffer: unmap everywhere before anybody frees
+                import torch.distributed as dist
+                self.lib.abm_sync(self.h)
+                if dist.is_initialized():
+                    dist.barrier()
+                self.lib.abm_peer_detach(self.h)
+                if dist.is_initialized():
+                    dist.barrier()
             self.lib.abm_destroy(self.h)
             self.h = None
 

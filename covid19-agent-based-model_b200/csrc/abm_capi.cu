@@ -11,6 +11,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -41,6 +42,12 @@ struct abm_handle {
     unsigned long long* acc_sum = nullptr;             // [2][P][A] replicas (and ranks) summed: tables of the last sub-step
     unsigned long long* acc_local = nullptr;           // [2][P][A] this rank's replicas summed, kept across incremental sub-steps
     bool tables_valid = false;                         // acc_local / hbig hold the sums of sub-step k - 1
+    int n_sms = 1;
+    // peer-memory exchange
+    unsigned long long* xchg_self = nullptr;           // exported buffer: data [2][2][P][A] u64, flags [2][P] u32
+    unsigned long long* xchg[ABM_MAX_RANKS] = {};      // every rank's buffer as mapped in this process
+    bool peers_attached = false;
+    unsigned int* rows_done = nullptr;
     int32_t replicas = 1;
     uint32_t* thr_out = nullptr;        // [P][A]
     unsigned long long* hbig[2] = {nullptr, nullptr};
@@ -146,6 +153,12 @@ DevWork make_work(const abm_handle* h) {
     w.daylog = h->daylog;
     w.rep_mask = (uint32_t)h->replicas - 1u;
     w.max_log_rows = h->cfg.max_log_rows;
+    w.rows_done = h->rows_done;
+    w.n_ranks = 1; w.rank = 0;
+    if (h->peers_attached) {
+        w.n_ranks = h->cfg.world_size; w.rank = h->cfg.rank;
+        for (int r = 0; r < h->cfg.world_size; ++r) w.xchg[r] = h->xchg[r];
+    }
     return w;
 }
 
@@ -163,7 +176,7 @@ int launch_main(abm_handle* h, uint32_t mode) {
         h->prof_used++;
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
-    const dim3 grid((unsigned)h->cfg.n_tiles), block(THREADS);
+    const dim3 grid((unsigned)(h->cfg.n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS)), block(THREADS);    // one warp per sub-tile
     uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
     const uint32_t rt_bits = (mode & M_STEP) ? 0u : M_NO_EARLY_DEPENDENTS;   // a flush is followed by a sub-step kernel, not a table kernel
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
@@ -224,6 +237,8 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
         h->prof_table_used++;
         CUDA_TRY(h, cudaEventRecord(t0, h->stream));
     }
+    if (c.world_size > 1 && c.exchange == 1 && !h->peers_attached)
+        return fail(h, ABM_ERR_STATE, "exchange == 1 needs abm_peer_attach before the first step");
     if (h->comm) {
         ta.do_reduce = 1; ta.do_threshold = 0;
         CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools), dim3(TABLE_THREADS), h->stream, c.use_pdl != 0, h->T, w, h->clock, ta));
@@ -344,6 +359,7 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(h, ABM_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
     CUDA_TRY(h, cudaSetDevice(cfg->device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     h->stream = (cudaStream_t)cfg->stream;
     if (!h->stream) {                        // the legacy default stream cannot be captured into a graph
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -364,6 +380,7 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if ((rc = alloc_zero(h, (size_t)h->replicas * N_TALLY, &h->tally))) return rc;
     if ((rc = alloc_zero(h, (size_t)12, &h->counters))) return rc;
     if ((rc = alloc_zero(h, (size_t)1, &h->clock))) return rc;
+    if ((rc = alloc_zero(h, (size_t)1, &h->rows_done))) return rc;
     {
         DevClock clk{};
         clk.k = 0; clk.now = 0; clk.minute_abs = cfg->start_minute_of_day; clk.weekday0 = cfg->start_weekday;
@@ -372,7 +389,13 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
     if ((rc = alloc_zero(h, (size_t)(cfg->max_log_rows + 1) * ABM_LOG_STRIDE, &h->daylog))) return rc;
-    if (cfg->world_size > 1) {
+    if (cfg->world_size > 1 && cfg->exchange == 1) {
+        if (cfg->world_size > ABM_MAX_RANKS) return fail(h, ABM_ERR_ARG, "peer exchange supports at most %d ranks", ABM_MAX_RANKS);
+        // exported to the peers with cudaIpcGetMemHandle: its own allocation (not part of `owned`, freed after detach)
+        const size_t words = (size_t)4 * pa + ((size_t)2 * cfg->n_pools * sizeof(unsigned int) + 7) / 8;
+        CUDA_TRY(h, cudaMalloc(&h->xchg_self, words * sizeof(unsigned long long)));
+        CUDA_TRY(h, cudaMemsetAsync(h->xchg_self, 0, words * sizeof(unsigned long long), h->stream));
+    } else if (cfg->world_size > 1) {
         if (!cfg->nccl_unique_id) return fail(h, ABM_ERR_ARG, "world_size > 1 needs an ncclUniqueId");
         h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h->nccl_lib) return fail(h, ABM_ERR_NCCL, "dlopen libnccl.so.2: %s", dlerror());
@@ -701,6 +724,52 @@ int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTER
     return ABM_OK;
 }
 
+int abm_peer_export(abm_handle* h, void* out_handle) {
+    if (!h || !out_handle) return ABM_ERR_ARG;
+    if (!h->xchg_self) return fail(h, ABM_ERR_STATE, "no exchange buffer (world_size > 1 and exchange == 1 required)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == ABM_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->xchg_self));
+    memcpy(out_handle, &mh, sizeof mh);
+    return ABM_OK;
+}
+
+int abm_peer_attach(abm_handle* h, const void* handles, int32_t n_ranks) {
+    if (!h || !handles) return ABM_ERR_ARG;
+    if (!h->xchg_self || n_ranks != h->cfg.world_size) return fail(h, ABM_ERR_ARG, "abm_peer_attach: %d handles for world size %d", n_ranks, h->cfg.world_size);
+    if (h->peers_attached) return fail(h, ABM_ERR_STATE, "peers already attached");
+    const char* bytes = static_cast<const char*>(handles);
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == h->cfg.rank) { h->xchg[r] = h->xchg_self; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, bytes + (size_t)r * ABM_IPC_HANDLE_BYTES, sizeof mh);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != h->cfg.rank && h->xchg[q]) { cudaIpcCloseMemHandle(h->xchg[q]); h->xchg[q] = nullptr; }
+            return fail(h, ABM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        h->xchg[r] = static_cast<unsigned long long*>(p);
+    }
+    h->peers_attached = true;
+    if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }
+    return ABM_OK;
+}
+
+int abm_peer_detach(abm_handle* h) {
+    if (!h) return ABM_ERR_ARG;
+    if (!h->peers_attached) return ABM_OK;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }    // kernel arguments hold the mapped pointers
+    for (int r = 0; r < h->cfg.world_size; ++r) {
+        if (r != h->cfg.rank && h->xchg[r]) cudaIpcCloseMemHandle(h->xchg[r]);
+        h->xchg[r] = nullptr;
+    }
+    h->peers_attached = false;
+    return ABM_OK;
+}
+
 int abm_table_time(abm_handle* h, double* total_ms) {
     if (!h || !total_ms) return ABM_ERR_ARG;
     int rc = collect_profile(h);
@@ -722,6 +791,8 @@ void abm_destroy(abm_handle* h) {
     if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
     for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : h->prof_table_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    abm_peer_detach(h);
+    if (h->xchg_self) cudaFree(h->xchg_self);
     for (void* p : h->owned) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;

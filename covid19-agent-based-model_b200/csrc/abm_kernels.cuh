@@ -79,11 +79,14 @@ enum { CUM_CONTAGIOUS = 0, CUM_INFECTED, CUM_HOSPITALIZED, CUM_CRITICAL, CUM_DIE
        PRE_EXPOSED, PRE_CONTAGIOUS, PRE_HOSPITALIZED, PRE_CRITICAL,
        POST_EXPOSED, POST_CONTAGIOUS, POST_HOSPITALIZED, POST_CRITICAL, N_TALLY };
 
-constexpr int THREADS = 256;
+#ifndef ABM_THREADS
+#define ABM_THREADS 128          // threads per CTA of the sub-step kernel: one warp per sub-tile, ABM_THREADS / 32 sub-tiles per CTA
+#endif
+constexpr int THREADS = ABM_THREADS;
 constexpr int WARPS = THREADS / 32;
 constexpr int PER_LANE = 4;
 constexpr int SUB = ABM_SUBTILE;
-static_assert(WARPS * SUB == ABM_TILE && PER_LANE * 32 == SUB, "one sub-tile per warp, one tile per block");
+static_assert(ABM_TILE % (WARPS * SUB) == 0 && PER_LANE * 32 == SUB, "one sub-tile per warp, whole CTAs per tile");
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 struct DevTables {
@@ -118,7 +121,13 @@ struct DevWork {
     long long* daylog;              // [max_log_rows + 1][ABM_LOG_STRIDE]
     uint32_t rep_mask;
     int32_t max_log_rows;
+    // multi-GPU exchange through peer memory (one node, NVLink / NVSwitch): every rank owns an exchange buffer
+    // that its peers map; layout in 64-bit words: data [2 parities][2][P][A], then 32-bit flags [2 parities][P]
+    unsigned long long* xchg[ABM_MAX_RANKS];   // xchg[r] = rank r's buffer as mapped here (own buffer at index `rank`)
+    unsigned int* rows_done;        // table-kernel rows finished in the current launch
+    int32_t n_ranks, rank;          // n_ranks > 1 only when the peer exchange is active
 };
+
 
 // The simulation clock lives in device memory and is advanced by the table kernel, so a whole simulated
 // day (6 x [sub-step kernel, table kernel]) is one replayable CUDA graph with no per-launch arguments.
@@ -131,6 +140,8 @@ struct __align__(16) DevClock {
     int32_t n_log_rows;
     long long seeds_before;   // seeded infections with tick < now     (base_model.py:796 + :1090)
     long long seeds_at_now;   // seeded at the current tick
+    uint32_t xchg_gen;        // table-kernel launches so far: generation tag of the peer exchange (never reset)
+    int32_t xchg_error;       // a peer did not publish its rows in time
 };
 
 struct StepArgs {
@@ -157,6 +168,22 @@ __device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock
 // predecessor has completed and its memory is visible.  Both are no-ops for a normally serialised launch.
 __device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// system-scope accesses for memory shared with peer GPUs
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 
 // ------------------------------------------------------------------------------------------------ Philox
 struct U4 { uint32_t x, y, z, w; };
@@ -525,6 +552,15 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
     uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
     bool dirty = false;
+    // return ticks of the travellers among the four agents (movement sub-steps only): requested now so the DRAM round
+    // trip overlaps the infection and transition phases instead of stalling the movement phase
+    int32_t tr0 = T_NEVER, tr1 = T_NEVER, tr2 = T_NEVER, tr3 = T_NEVER;
+    if (mode_static & (M_GO_OUT | M_GO_HOME)) {
+        if (f0 & F_AWAY) tr0 = G.t_return[slot0 + 0];
+        if (f1 & F_AWAY) tr1 = G.t_return[slot0 + 1];
+        if (f2 & F_AWAY) tr2 = G.t_return[slot0 + 2];
+        if (f3 & F_AWAY) tr3 = G.t_return[slot0 + 3];
+    }
     uint32_t* hz = s_hz[wid];
     unsigned int* acc_w = s_acc[wid];
 
@@ -663,7 +699,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_GO_HOME(f3, 8u)
 #undef ABM_GO_HOME
             ABM_LANE_LOOP_RW(away, {
-                if (G.t_return[slot0 + J] < s.now) {                                    // :285-293
+                if ((J == 0 ? tr0 : (J == 1 ? tr1 : (J == 2 ? tr2 : tr3))) < s.now) {   // :285-293
                     aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
                     fj = fj & ~(F_AWAY | LOCF);
                 }
@@ -710,7 +746,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             // travellers: back in the home district when the stay is over (:342-360), then like everybody else
             ABM_LANE_LOOP_RW(away, {
                 bool out_again = false;
-                if (G.t_return[slot0 + J] < s.now) {
+                if ((J == 0 ? tr0 : (J == 1 ? tr1 : (J == 2 ? tr2 : tr3))) < s.now) {
                     aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
                     fj &= ~F_AWAY;
                     const uint32_t u = word_of(XO, J) >> 1;
@@ -852,6 +888,10 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
 //   reduce     sum the replicas of row L of the tables of the sub-step just executed into acc_sum and
 //              clear the row in every replica of the OTHER buffer (used by the next sub-step)
 //   threshold  thresholds of row L from acc_sum (after the all-reduce over ranks when there is one)
+// With several ranks on one node the sum over ranks is part of this kernel: block L publishes its row in the rank's
+// exchange buffer (release, system scope), waits for the same row of every peer (acquire) and adds them up through
+// peer loads over NVLink -- 2 A words per peer and row, no separate collective, no extra launch.  (Across nodes, or
+// when peer mapping is unavailable, the rows go through ncclAllReduce between a reduce and a threshold launch.)
 // Block P (the last one) folds the per-launch tallies into the running counters and, at log sub-steps,
 // writes the day-log row: cumulative date counters include this sub-step's transitions, the "current"
 // counters are taken before them (base_model.py:36-38: log_model_output runs before update_agent_states).
@@ -873,6 +913,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
     const int k = clk->k;                               // the sub-step that was just executed
+    const unsigned int gen = clk->xchg_gen + 1u;        // block P advances both only after every row block is done
     if (L < T.P) {
         const unsigned long long* __restrict__ acc = (k & 1) ? Wk.acc2[1] : Wk.acc2[0];
         unsigned long long* __restrict__ acc_next = (k & 1) ? Wk.acc2[0] : Wk.acc2[1];
@@ -897,9 +938,34 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
                 Wk.acc_local[off] = sum;
                 Wk.acc_sum[off] = sum;
                 s_row[t] = sum;
+                if (Wk.n_ranks > 1) Wk.xchg[Wk.rank][(size_t)(gen & 1u) * 2 * n + off] = sum;
             }
         } else if (t < 2 * A) {
             s_row[t] = Wk.acc_sum[off];
+        }
+        if (Wk.n_ranks > 1 && ta.do_reduce) {
+            // ---- sum over ranks through peer memory
+            const size_t flag_words = (size_t)4 * n;                    // flags start after the two data parities
+            __threadfence_system();
+            __syncthreads();
+            if (t == 0)
+                st_release_sys(reinterpret_cast<unsigned int*>(Wk.xchg[Wk.rank] + flag_words) + (gen & 1u) * T.P + L, gen);
+            if (t < Wk.n_ranks && t != Wk.rank) {
+                const unsigned int* flag = reinterpret_cast<const unsigned int*>(Wk.xchg[t] + flag_words) + (gen & 1u) * T.P + L;
+                int spins = 0;
+                while ((int)(ld_acquire_sys(flag) - gen) < 0) {
+                    if (++spins > (1 << 22)) { clk->xchg_error = 1; break; }     // a peer is gone: do not hang the GPU
+                    __nanosleep(64);
+                }
+            }
+            __syncthreads();
+            if (t < 2 * A) {
+                unsigned long long total = s_row[t];
+                for (int r = 0; r < Wk.n_ranks; ++r)
+                    if (r != Wk.rank) total += ld_relaxed_sys(Wk.xchg[r] + (size_t)(gen & 1u) * 2 * n + off);
+                Wk.acc_sum[off] = total;
+                s_row[t] = total;
+            }
         }
         __syncthreads();
         if (ta.do_threshold && t < A) {
@@ -916,6 +982,8 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             }
             Wk.thr_out[L * A + t] = thr;
         }
+        __syncthreads();
+        if (t == 0 && ta.do_threshold) { __threadfence(); atomicAdd(Wk.rows_done, 1u); }
         return;
     }
     if (!ta.do_threshold) return;         // the bookkeeping below runs once per sub-step, with the thresholds
@@ -965,6 +1033,10 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
     }
     __syncthreads();
     if (t == 0) {                         // advance the clock (base_model.py:177-179)
+        // ... once every row block has read it (they are dispatched before this block and never wait for it)
+        while (atomicAdd(Wk.rows_done, 0u) < (unsigned int)T.P) __nanosleep(32);
+        *Wk.rows_done = 0u;
+        clk->xchg_gen = gen;
         const int minute_abs = clk->minute_abs + T.step_ticks;
         clk->k = k + 1;
         clk->now = now + T.step_ticks;

@@ -31,6 +31,8 @@ extern "C" {
 #define ABM_OMEXP_N 8192         /* entries of the 1 - exp(-i/256) table (hazards up to 32)        */
 #define ABM_N_COUNTERS 12        /* fields of Country.log_model_output (base_model.py:1086-1104)   */
 #define ABM_LOG_STRIDE 16        /* int64 words per day-log row                                    */
+#define ABM_MAX_RANKS 16         /* ranks of one node that can share tables through peer memory    */
+#define ABM_IPC_HANDLE_BYTES 64  /* size of the opaque handle abm_peer_export produces             */
 
 typedef enum {
     ABM_OK = 0,
@@ -84,7 +86,11 @@ typedef struct {
     int32_t use_pdl;            /* programmatic dependent launch: the next kernel's prologue overlaps the table kernel */
     int32_t world_size;         /* ranks sharing the district tables (1 = no collective)            */
     int32_t rank;
-    const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1            */
+    const void* nccl_unique_id; /* 128-byte ncclUniqueId from rank 0 when world_size > 1 and exchange == 0 */
+    int32_t exchange;           /* how the district x status tables are summed over ranks: 0 = ncclAllReduce between two */
+                                /* table launches; 1 = inside the table kernel through peer memory (one node; needs      */
+                                /* abm_peer_export / abm_peer_attach before the first step)                              */
+    int32_t reserved;
 } abm_config;
 
 /* Host pointers to the derived constant tables (abm_b200/tables.py); copied to the device. */
@@ -169,6 +175,13 @@ void abm_destroy(abm_handle* h);
 int abm_version(void);
 /* ncclGetUniqueId into a 128-byte buffer (rank 0 calls it and broadcasts the bytes out of band). */
 int abm_nccl_unique_id(void* out128);
+/* Peer-memory exchange (abm_config.exchange == 1): every rank exports the handle of its exchange buffer
+ * (ABM_IPC_HANDLE_BYTES bytes), the caller gathers the handles of all ranks in rank order (any out-of-band
+ * transport) and hands them to abm_peer_attach, which maps the peers' buffers.  abm_peer_detach unmaps them; call
+ * it on every rank, then synchronise the ranks, before abm_destroy frees the exported buffer. */
+int abm_peer_export(abm_handle* h, void* out_handle);
+int abm_peer_attach(abm_handle* h, const void* handles, int32_t n_ranks);
+int abm_peer_detach(abm_handle* h);
 
 #ifdef __cplusplus
 }

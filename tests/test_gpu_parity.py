@@ -185,3 +185,56 @@ def test_checkpoint_restore_resumes_identically(built_library):
     assert la[-len(lb):] == lb and len(lb) == 6
     assert a.counters() == b.counters()
     a.close(); b.close()
+
+
+def test_five_hundred_districts(built_library):
+    """BASELINE.json configs[4] shape: 500 districts (OD rows of 500 columns, 500-row tables), small population."""
+    spec = synth.make_spec(n_districts=500, R0=2.6, seed=51)
+    pop = synth.make_population(60_000, spec, seed=51)
+    seeds = synth.pick_seeds(pop, spec, infect_num=400, seed=51, cases=synth.seed_case_counts(pop, spec, seed=51, n_seed_districts=40))
+    tab = tables.build_tables(spec)
+    sim = _sim(spec, pop, 15, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 15)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    sim.step(6 * 12)
+    for _ in range(6 * 12):
+        ora.step()
+    assert_state_equal(sim.state(), ora.state_dict(), '500 districts, 12 days')
+    r, n, t = sim.debug_tables()
+    assert np.array_equal(r, ora.last_tables['rsum']) and np.array_equal(n, ora.last_tables['ncnt'])
+    assert np.array_equal(t, ora.last_tables['thr_out'])
+    assert (ora.current_district_ids != ora.district_ids).sum() > 100       # travellers are under way
+    sim.close()
+
+
+def test_population_conservation_and_monotone_counters_at_scale(built_library):
+    """Size-independent properties on a 2 M-agent population (too big for the oracle to follow in seconds): nobody is
+    lost or duplicated, cumulative counters never decrease, the state machine only moves forward, and the running
+    counters agree with an independent recount of the agent store."""
+    spec = synth.make_spec(n_districts=60, R0=2.4, seed=61)
+    pop = synth.make_population(2_000_000, spec, seed=61)
+    seeds = synth.pick_seeds(pop, spec, infect_num=4000, seed=61)
+    sim = _sim(spec, pop, 21)
+    sim.seed_infections(seeds)
+    prev = sim.state()['epidemic_state'].astype(np.int64)
+    for _ in range(4):
+        sim.step(6 * 10)
+        st = sim.state()
+        epi = st['epidemic_state'].astype(np.int64)
+        assert epi.shape[0] == pop.n and epi.min() >= 0 and epi.max() <= 4
+        assert np.all(epi >= prev)                                   # S -> I -> C -> R / D never goes back
+        assert np.all((st['current_location_ids'] >= -spec.n_districts))
+        dead = epi == 4
+        assert np.all(st['current_location_ids'][dead] == -1) and np.all(st['clinical_state'][dead] == 3)
+        infected = st['date_infected'] != 2 ** 31 - 1
+        assert np.array_equal(infected, epi > 0)
+        c = sim.counters()
+        assert c['current_exposed_cases'] == int((epi == 1).sum()) and c['current_contagious_cases'] == int((epi == 2).sum())
+        assert c['asymptomatic_count'] + c['symptomatic_count'] == int(infected.sum())
+        prev = epi
+    log = sim.read_log()
+    for col in (0, 1, 2, 3, 4, 5, 10, 11):                          # cumulative columns of the day log
+        assert np.all(np.diff(log[:, col]) >= 0), col
+    assert log[-1, 1] > 100_000
+    sim.close()

@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--agents', type=int, default=120_000)
     ap.add_argument('--districts', type=int, default=8)
     ap.add_argument('--days', type=int, default=20)
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'])
     a = ap.parse_args()
 
     import torch
@@ -45,9 +46,10 @@ def main():
     lo, hi = sharding.split_population(pop, world)[rank]
     shard = sharding.slice_population(pop, lo, hi)
     dstart = np.searchsorted(pop.district, np.arange(spec.n_districts + 1)).astype(np.int64)
-    uid = distributed.exchange_unique_id(lib, rank, world, device) if world > 1 else None
+    uid = distributed.exchange_unique_id(lib, rank, world, device) if (world > 1 and a.exchange == 'nccl') else None
     sim = Simulation(spec, shard, seed=4242, device=local, tables=tab, agent_id_base=lo, district_start=dstart,
-                     world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4)
+                     world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4,
+                     exchange=a.exchange if world > 1 else None)
     sim.seed_infections(seeds[(seeds >= lo) & (seeds < hi)])
     sim.step(6 * a.days)
 
@@ -86,7 +88,7 @@ def main():
           f'mismatches {bad}', flush=True)
     failed = int(flag.item()) != 0
     if rank == 0 and not failed:
-        print(f'multi_gpu_check ok: world {world}, {a.agents} agents, {a.days} days, '
+        print(f'multi_gpu_check ok ({a.exchange if world > 1 else "single rank"}): world {world}, {a.agents} agents, {a.days} days, '
               f'infected_count {ora.log_rows[-1]["infected_count"]}', flush=True)
 
     import threading
