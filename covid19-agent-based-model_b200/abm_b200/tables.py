@@ -78,8 +78,12 @@ def move_classes(pop: Population, mild_prob: float):
     (weekday healthy, weekday mild-symptom, other-day healthy, other-day mild-symptom); each
     threshold is ceil((p * mild) * 2^31), the product taken in float64 exactly as
     base_model.py:318 does."""
-    pairs = np.stack([pop.move_prob_weekday, pop.move_prob_other], axis=1)
-    uniq, inv = np.unique(pairs, axis=0, return_inverse=True)
+    # few distinct values per column: encode each column by itself (1-D), then the pairs of small codes
+    uw, iw = np.unique(pop.move_prob_weekday, return_inverse=True)
+    uo, io = np.unique(pop.move_prob_other, return_inverse=True)
+    pair_code = iw.astype(np.int64) * uo.shape[0] + io
+    codes, inv = np.unique(pair_code, return_inverse=True)
+    uniq = np.stack([uw[codes // uo.shape[0]], uo[codes % uo.shape[0]]], axis=1)
     if uniq.shape[0] > 65535:
         raise ValueError('more than 65535 distinct movement-probability pairs')
     thr = np.stack([bern_threshold(uniq[:, 0] * 1.0), bern_threshold(uniq[:, 0] * mild_prob),

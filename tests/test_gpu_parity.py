@@ -238,3 +238,24 @@ def test_population_conservation_and_monotone_counters_at_scale(built_library):
         assert np.all(np.diff(log[:, col]) >= 0), col
     assert log[-1, 1] > 100_000
     sim.close()
+
+
+def test_ensemble_replicas_equal_individual_runs(built_library):
+    """Members run concurrently on their own streams (abm_b200.ensemble) give exactly the curves of one-at-a-time runs."""
+    from abm_b200 import ensemble
+    from abm_b200.engine import COUNTER_NAMES
+    spec, pop, seeds, tab = small_case(n_agents=30_000, seed=27)
+    keys = [101, 202, 303, 404, 505]
+    seed_sets = [synth.pick_seeds(pop, spec, infect_num=200, seed=s) for s in range(5)]
+    curves, dates = ensemble.run_ensemble(spec, pop, seed_sets, keys, days=12, max_concurrent=3, tables=tab)
+    assert curves.shape == (5, 12, 12) and len(dates) == 12
+    for m in (0, 3, 4):
+        sim = _sim(spec, pop, keys[m], tab)
+        sim.seed_infections(seed_sets[m])
+        sim.step(6 * 12)
+        assert np.array_equal(sim.read_log()[:, :12], curves[m]), m
+        sim.close()
+    assert not np.array_equal(curves[0], curves[1])
+    band = ensemble.summarize(curves)
+    assert band['mean'].shape == (12, 12) and np.all(band['lo'] <= band['hi'])
+    assert curves[:, -1, COUNTER_NAMES.index('infected_count')].min() > 200
