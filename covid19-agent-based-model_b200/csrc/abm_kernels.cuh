@@ -526,7 +526,6 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     __shared__ int s_home[WARPS];
     __shared__ unsigned int s_done;
 
-    if (!(mode_rt & M_NO_EARLY_DEPENDENTS)) launch_dependents();   // the table kernel may become resident; it waits for this grid
     const uint32_t mode_static = MODE == RUNTIME_MODE ? (mode_rt & 0xFFFFu) : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t sub = blockIdx.x * WARPS + wid;
@@ -597,6 +596,10 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     // before the table kernel started.  From here on the outputs of the table kernel are needed: thresholds,
     // cleared accumulators, the advanced clock.
     grid_dependency_wait();
+    // The table kernel may become resident now; it waits for this grid before it reads what the grid writes.  (Only
+    // after the wait above: everything the table kernel reads early was written by its predecessor, which every CTA
+    // of this grid has now seen complete.)
+    if (!(mode_rt & M_NO_EARLY_DEPENDENTS)) launch_dependents();
     const StepArgs s = step_args(T, clk, mode_static);
     const uint32_t mode = s.mode;
     unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
@@ -908,22 +911,34 @@ __global__ void __launch_bounds__(TABLE_THREADS)
 abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restrict__ clk, const TableArgs ta) {
     __shared__ unsigned long long s_part[TABLE_THREADS / 32][32];
     __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
-    grid_dependency_wait();       // the sub-step kernel has completed: its atomics are visible
-    launch_dependents();          // the next sub-step kernel may start its table-independent prologue
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
-    const int k = clk->k;                               // the sub-step that was just executed
+    // ---- before the dependency wait: everything that only this kernel's predecessor (the previous table kernel)
+    // or the host wrote -- the clock, the kept sums, constants.  These loads overlap the tail of the sub-step kernel.
+    const int k = clk->k;                               // the sub-step that is being executed by the primary grid
     const unsigned int gen = clk->xchg_gen + 1u;        // block P advances both only after every row block is done
+    const int e = t & 31, g = t >> 5;                   // entry e < A: pressure sum of status e; A <= e < 2A: head count
+    const size_t off = e < A ? (size_t)L * A + e : (size_t)n + (size_t)L * A + (e - A);
+    unsigned long long kept = 0ull;
+    double w_col[ABM_MAX_STATUS];
+    double hw_L = 0.0;
+    if (L < T.P) {
+        if (ta.do_reduce && ta.incremental && t < 2 * A) kept = Wk.acc_local[off];
+        if (ta.do_threshold && t < A) {
+#pragma unroll
+            for (int a = 0; a < ABM_MAX_STATUS; ++a) w_col[a] = a < A ? __ldg(T.W + a * A + t) : 0.0;
+            hw_L = __ldg(T.pool_hw + L);
+        }
+    }
+    grid_dependency_wait();       // the sub-step kernel has completed: its atomics are visible
+    launch_dependents();          // the next sub-step kernel may start its table-independent prologue
     if (L < T.P) {
         const unsigned long long* __restrict__ acc = (k & 1) ? Wk.acc2[1] : Wk.acc2[0];
         unsigned long long* __restrict__ acc_next = (k & 1) ? Wk.acc2[0] : Wk.acc2[1];
-        // entry e < A: pressure sum of status e; A <= e < 2A: head count of status e - A
-        const int e = t & 31, g = t >> 5;
-        const size_t off = e < A ? (size_t)L * A + e : (size_t)n + (size_t)L * A + (e - A);
         if (ta.do_reduce) {
             unsigned long long v = 0ull;
             if (e < 2 * A) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int r = g; r < ta.replicas; r += TABLE_THREADS / 32) {     // warp g sums every 8th replica
                     v += acc[(size_t)r * 2 * n + off];
                     acc_next[(size_t)r * 2 * n + off] = 0ull;
@@ -932,7 +947,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             s_part[g][e] = v;
             __syncthreads();
             if (t < 2 * A) {
-                unsigned long long sum = ta.incremental ? Wk.acc_local[off] : 0ull;
+                unsigned long long sum = kept;
 #pragma unroll
                 for (int w = 0; w < TABLE_THREADS / 32; ++w) sum += s_part[w][t];
                 Wk.acc_local[off] = sum;
@@ -973,9 +988,10 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             uint32_t thr = 0;
             if (cnt) {
                 double sum = 0.0;
-                for (int a = 0; a < A; ++a)
-                    sum = __dadd_rn(sum, __dmul_rn(__ldg(T.W + a * A + t), (double)s_row[a]));
-                const double lam = __dmul_rn(__ldg(T.pool_hw + L), __ddiv_rn(sum, (double)cnt));
+#pragma unroll
+                for (int a = 0; a < ABM_MAX_STATUS; ++a)
+                    if (a < A) sum = __dadd_rn(sum, __dmul_rn(w_col[a], (double)s_row[a]));
+                const double lam = __dmul_rn(hw_L, __ddiv_rn(sum, (double)cnt));
                 const unsigned long long h = lam >= (double)(ABM_OMEXP_N >> 8) ? ((unsigned long long)ABM_OMEXP_N << 24)
                                                                                : __double2ull_rz(__dmul_rn(lam, 4294967296.0));
                 thr = hazard_threshold_fx(T.omexp, h);

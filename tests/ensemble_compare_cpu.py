@@ -2,7 +2,7 @@
 """Build-container check of the tier-2 tolerance: run the ensemble through the drop-in package with the engine
 replaced by the oracle-backed test double (bit-identical to the CUDA path) and print the comparison with the
 stored reference ensembles.  Not part of any product path.
-    python tools/ensemble_compare_cpu.py unmitigated_100k 64"""
+    python tests/ensemble_compare_cpu.py unmitigated_100k 64"""
 import multiprocessing as mp
 import os
 import sys

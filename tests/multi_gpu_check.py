@@ -4,7 +4,7 @@ single-rank oracle trajectory bit for bit (draws are keyed by the global agent i
 the all-reduce of the district x status tables).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py [--agents 120000] [--days 20]
+        tests/multi_gpu_check.py [--agents 120000] [--days 20]
 
 Every rank runs the full-population oracle itself (test infrastructure, CPU) and compares its own shard.
 Exit code 0 and a line `multi_gpu_check ok` on rank 0 when all ranks agree.

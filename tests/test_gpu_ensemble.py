@@ -7,7 +7,7 @@ from the device's Philox stream).  Stated tolerance: for each of daily active (c
 dead and cumulative infected counts, the ensemble MEAN of the CUDA members lies inside the reference members' central
 95 % band (2.5th..97.5th percentile across members) on at least 95 % of the logged days, the two ensemble means never
 differ by more than 3.5 combined standard errors, and the final cumulative infected mean is within 5 % of the
-reference's.  (Measured with the bit-identical CPU oracle, tools/ensemble_compare_cpu.py: inside on 100 % of days,
+reference's.  (Measured with the bit-identical CPU oracle, tests/ensemble_compare_cpu.py: inside on 100 % of days,
 largest difference 2.2 standard errors, final infected +0.9 % unmitigated / -0.6 % lockdown.)  This bounds the one restated piece of the path -- the
 pressure-table form of the contact sampler -- and the table-based dwell-time sampling."""
 import os

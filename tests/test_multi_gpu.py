@@ -1,4 +1,4 @@
-"""Two ranks on two GPUs reproduce the single-rank oracle trajectory (tools/multi_gpu_check.py).
+"""Two ranks on two GPUs reproduce the single-rank oracle trajectory (tests/multi_gpu_check.py).
 Skipped on boxes with fewer than two GPUs; the host-side sharding logic is covered on CPU by
 tests/test_sharding_gloo.py."""
 import os
@@ -18,7 +18,7 @@ def test_two_ranks_match_single_rank_oracle(built_library, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
-           '127.0.0.1', '--master-port', '29533' if exchange == 'p2p' else '29534', os.path.join(ROOT, 'tools', 'multi_gpu_check.py'),
+           '127.0.0.1', '--master-port', '29533' if exchange == 'p2p' else '29534', os.path.join(ROOT, 'tests', 'multi_gpu_check.py'),
            '--agents', '80000', '--days', '12', '--exchange', exchange]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
