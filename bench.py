@@ -270,6 +270,7 @@ def run_cuda_arm(a):
         pinned = {name: torch.from_numpy(arr).pin_memory() for name, arr in ckpt['arrays'].items()}
         host_ckpt = dict(arrays=pinned, k=ckpt['k'], counters=ckpt['counters'], seeded=ckpt['seeded'])
         sim = make_sim(upload=False)          # handle, empty device buffers, constant tables, communicator: set-up, untimed
+        final_state = torch.empty(pinned['flags'].shape, dtype=pinned['flags'].dtype).pin_memory()   # page-locked landing buffer
         torch.cuda.synchronize(device)
         barrier()
         t0 = time.perf_counter()
@@ -280,8 +281,10 @@ def run_cuda_arm(a):
             sim.step(SUBSTEPS_PER_DAY)
             rows = sim.read_log()             # device -> host read of the day's counters (synchronises)
             d2h += 16 * 8
-        flags = sim.buf['flags'].cpu()        # final packed state
-        d2h += flags.numel() * flags.element_size()
+        with torch.cuda.stream(sim.stream):   # final packed state -> page-locked host memory
+            final_state.copy_(sim.buf['flags'], non_blocking=True)
+        sim.sync()
+        d2h += final_state.numel() * final_state.element_size()
         barrier()
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device=device)

@@ -62,3 +62,44 @@ def test_run_days_equals_single_steps(tmp_path):
     assert [r for r in dropin_flow.read_log(str(tmp_path / 'a.log'))] == [r for r in dropin_flow.read_log(str(tmp_path / 'b.log'))]
     assert a.scheduler.real_time == b.scheduler.real_time
     a.close(); b.close()
+
+
+def test_run_scenario_driver(tmp_path):
+    """The reference's own driver function (scenario_models.py:443-500): parameters, model, load + seed, step loop to
+    2021-06-01, log file, pickled model -- and the same trajectory as stepping the model by hand."""
+    import glob
+    import pickle
+    from datetime import timedelta
+    from covid19_abm import scenario_models
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    dropin_flow.build_world(root, n_agents=20_000)
+    start = datetime(2021, 5, 22, 0)
+    scenario_models.UnmitigatedScenario.philox_seed = 4711
+    try:
+        np.random.seed(5)
+        model = scenario_models.run_scenario(scenario_models.UnmitigatedScenario, 'Unmitigated', '3', 2.6, 100, 150,
+                                             start_date=start, timestep=timedelta(hours=4))
+        assert model.scheduler.real_time == datetime(2021, 6, 1, 4)          # first step past the end date
+        logs = glob.glob(os.path.join(root, 'logs', 'model_log_file_Unmitigated_03_R2.6_samp100_seed150.*.log'))
+        dumps = glob.glob(os.path.join(root, 'logs', 'model_dump_file_Unmitigated_03_R2.6_samp100_seed150.*.pickle'))
+        assert len(logs) == 1 and len(dumps) == 1
+        rows = dropin_flow.read_log(logs[0])
+        assert len(rows) == 10 and rows[0]['date'] == '2021-05-22T08:00:00' and rows[-1]['infected_count'] > 300
+        with open(dumps[0], 'rb') as fl:
+            again = pickle.load(fl)
+        assert again._sim is None and np.array_equal(again.epidemic_state, model.epidemic_state)
+        # by hand: same numpy seed, same Philox key, same number of sub-steps
+        np.random.seed(5)
+        p = dropin_flow.make_params(R0=2.6, seed_infected=150)
+        by_hand = scenario_models.UnmitigatedScenario(p, model_log_file=None)
+        p.SIMULATION_START_DATE = start
+        by_hand.scheduler.real_time = start
+        by_hand.load_agents(p.data_file_name, size=None, infect_num=p.SEED_INFECT_NUM)
+        for _ in range(model.scheduler.steps):
+            by_hand.step()
+        assert np.array_equal(by_hand.epidemic_state, model.epidemic_state)
+        assert np.array_equal(by_hand.event_ticks('date_recovered'), model.event_ticks('date_recovered'))
+        by_hand.close(); model.close()
+    finally:
+        scenario_models.UnmitigatedScenario.philox_seed = None
