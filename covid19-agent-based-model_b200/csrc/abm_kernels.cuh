@@ -484,14 +484,6 @@ constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
     }
 // Same, without the warp votes: a plain divergent loop (bodies without warp collectives); lanes leave as
 // soon as their own mask is empty and the warp reconverges behind the loop.
-#define ABM_LANE_LOOP(mask, ...)                                                     \
-    while (mask) {                                                                   \
-        const int J = __ffs(mask) - 1;                                               \
-        (mask) &= (mask) - 1u;                                                       \
-        const uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));        \
-        const uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));        \
-        __VA_ARGS__                                                                  \
-    }
 #define ABM_LANE_LOOP_RW(mask, ...)                                                  \
     while (mask) {                                                                   \
         const int J = __ffs(mask) - 1;                                               \
@@ -629,22 +621,20 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
                 ABM_OUT_THR(f3, a3, r3, t3, 8u)
 #undef ABM_OUT_THR
             } else {
-                // night: only travellers and the few agents of quirk Q4 are in an outside pool
-                uint32_t look = 0;
-#define ABM_OUT_THR(fj, bit)                                                                         \
+                // night: only travellers and the few agents of quirk Q4 are in an outside pool.  Straight-line,
+                // predicated look-ups (the four loads are in flight together; no divergent loop to resolve).
+#define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
                 if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
-                    if ((((fj) & LOCF) - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) look |= (bit); else odd |= (bit); \
+                    const uint32_t lf = (fj) & LOCF;                                                 \
+                    if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL))                               \
+                        tj = __ldg(Wk.thr_out + (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj)); \
+                    else odd |= (bit);                                                               \
                 }
-                ABM_OUT_THR(f0, 1u)
-                ABM_OUT_THR(f1, 2u)
-                ABM_OUT_THR(f2, 4u)
-                ABM_OUT_THR(f3, 8u)
+                ABM_OUT_THR(f0, a0, t0, 1u)
+                ABM_OUT_THR(f1, a1, t1, 2u)
+                ABM_OUT_THR(f2, a2, t2, 4u)
+                ABM_OUT_THR(f3, a3, t3, 8u)
 #undef ABM_OUT_THR
-                ABM_LANE_LOOP(look, {
-                    const uint32_t pool = (fj & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0;
-                    const uint32_t thr = __ldg(Wk.thr_out + pool * A + status_of(fj));
-                    if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
-                })
             }
             ABM_FUNNEL_RO(odd, {
                 uint32_t thr = 0;
@@ -701,12 +691,17 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_GO_HOME(f2, 4u)
             ABM_GO_HOME(f3, 8u)
 #undef ABM_GO_HOME
-            ABM_LANE_LOOP_RW(away, {
-                if ((J == 0 ? tr0 : (J == 1 ? tr1 : (J == 2 ? tr2 : tr3))) < s.now) {   // :285-293
-                    aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
-                    fj = fj & ~(F_AWAY | LOCF);
-                }
-            })
+#define ABM_BACK_HOME(fj, aj, trj, bit)                                                              \
+            if ((away & (bit)) && (trj) < s.now) {                                      /* :285-293 */  \
+                aj = ((aj) & 0xFFFF0000u) | (uint32_t)L0;                                            \
+                fj = (fj) & ~(F_AWAY | LOCF);                                                        \
+                dirty = true;                                                                        \
+            }
+            ABM_BACK_HOME(f0, a0, tr0, 1u)
+            ABM_BACK_HOME(f1, a1, tr1, 2u)
+            ABM_BACK_HOME(f2, a2, tr2, 4u)
+            ABM_BACK_HOME(f3, a3, tr3, 8u)
+#undef ABM_BACK_HOME
         }
         if (mode & M_GO_OUT) {                                                          // :304-340
             const uint2 mc = *reinterpret_cast<const uint2*>(G.move_class + slot0);
@@ -800,11 +795,17 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_COUNT(f2, 4u)
             ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
-            ABM_LANE_LOOP(dest, {
-                const uint32_t e = cur_of(aj) * A + status_of(fj);
-                atomicAdd(acc_n + e, 1ull);
-                if ((fj & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
-            })
+#define ABM_ADD_DEST(fj, aj, bit)                                                                    \
+            if (dest & (bit)) {                                                                      \
+                const uint32_t e = cur_of(aj) * A + status_of(fj);                                   \
+                atomicAdd(acc_n + e, 1ull);                                                          \
+                if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+            }
+            ABM_ADD_DEST(f0, a0, 1u)
+            ABM_ADD_DEST(f1, a1, 2u)
+            ABM_ADD_DEST(f2, a2, 4u)
+            ABM_ADD_DEST(f3, a3, 8u)
+#undef ABM_ADD_DEST
             const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
             const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
             const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
@@ -828,11 +829,17 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_COUNT(f2, 4u)
             ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
-            ABM_LANE_LOOP(pooled, {
-                const uint32_t e = ((fj & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj);
-                atomicAdd(acc_n + e, 1ull);
-                if ((fj & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
-            })
+#define ABM_ADD_POOLED(fj, aj, bit)                                                                  \
+            if (pooled & (bit)) {                                                                    \
+                const uint32_t e = (((fj) & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj); \
+                atomicAdd(acc_n + e, 1ull);                                                          \
+                if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+            }
+            ABM_ADD_POOLED(f0, a0, 1u)
+            ABM_ADD_POOLED(f1, a1, 2u)
+            ABM_ADD_POOLED(f2, a2, 4u)
+            ABM_ADD_POOLED(f3, a3, 8u)
+#undef ABM_ADD_POOLED
         }
         ABM_FUNNEL_RO(work, {
             const int pool = pool_of(G, fj, aj, slot0 + J, L0);
