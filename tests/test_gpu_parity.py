@@ -259,3 +259,67 @@ def test_ensemble_replicas_equal_individual_runs(built_library):
     band = ensemble.summarize(curves)
     assert band['mean'].shape == (12, 12) and np.all(band['lo'] <= band['hi'])
     assert curves[:, -1, COUNTER_NAMES.index('infected_count')].min() > 200
+
+
+@pytest.mark.parametrize('step_minutes,start', [(120, (2020, 9, 1, 8)), (480, (2020, 9, 1, 0)), (240, (2020, 9, 1, 8)),
+                                                (60, (2020, 9, 4, 22))])
+def test_other_time_steps_and_start_hours(built_library, step_minutes, start):
+    """The sub-step need not be 4 h and the run need not start at midnight (the reference's default start is 08:00,
+    params.py:369): 2 h (12 sub-steps a day), 8 h (an odd number: 3), 1 h starting on a Friday night."""
+    from datetime import datetime
+    spec = synth.make_spec(n_districts=5, R0=3.0, seed=71, start_datetime=datetime(*start), step_minutes=step_minutes)
+    pop = synth.make_population(12_000, spec, seed=71)
+    seeds = synth.pick_seeds(pop, spec, infect_num=200, seed=71)
+    tab = tables.build_tables(spec)
+    sim = _sim(spec, pop, 33, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 33)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    per_day = 1440 // step_minutes
+    n = per_day * 8 + 5
+    sim.step(n)
+    for _ in range(n):
+        ora.step()
+    assert_state_equal(sim.state(), ora.state_dict(), f'{step_minutes} min steps from {start}')
+    got = sim.log_dicts()
+    assert len(got) == len(ora.log_rows) and len(got) >= 8
+    for g, w in zip(got, ora.log_rows):
+        for key, val in w.items():
+            assert g[key] == val, (key, g['date'])
+    sim.close()
+
+
+@pytest.mark.parametrize('n_agents,n_districts', [(300, 1), (1100, 2), (4099, 3)])
+def test_tiny_and_ragged_populations(built_library, n_agents, n_districts):
+    """One district, populations smaller than a tile, agent counts that leave ragged last sub-tiles."""
+    spec = synth.make_spec(n_districts=n_districts, R0=4.0, seed=81)
+    pop = synth.make_population(n_agents, spec, seed=81)
+    rng = np.random.default_rng(81)
+    eligible = np.nonzero((pop.age > 20) & (pop.age < 60))[0]
+    seeds = np.sort(rng.choice(eligible, size=min(25, eligible.shape[0]), replace=False)).astype(np.int64)
+    tab = tables.build_tables(spec)
+    sim = _sim(spec, pop, 44, tab)
+    ora = OracleModel(pop, oracle_params(spec), tab, 44)
+    sim.seed_infections(seeds)
+    ora.set_epidemic_status(seeds)
+    for _ in range(5):
+        sim.step(6 * 4)
+        for _ in range(6 * 4):
+            ora.step()
+        assert_state_equal(sim.state(), ora.state_dict(), f'{n_agents} agents, {n_districts} district(s)')
+    assert sim.read_log().shape[0] == 20
+    sim.close()
+
+
+def test_no_infection_and_empty_seed_list(built_library):
+    """Nothing seeded: nobody is ever infected, people still move; seeding an empty list is a no-op."""
+    spec, pop, _, tab = small_case(n_agents=9000, seed=91)
+    sim = _sim(spec, pop, 1, tab)
+    sim.seed_infections(np.zeros(0, dtype=np.int64))
+    sim.step(6 * 3 + 3)                               # stop at noon: people are out
+    st = sim.state()
+    assert not st['epidemic_state'].any() and np.all(st['date_infected'] == 2 ** 31 - 1)
+    assert (st['current_location_ids'] < spec.n_districts).sum() > 5000
+    log = sim.log_dicts()
+    assert len(log) == 4 and all(r['infected_count'] == 0 and r['current_contagious_cases'] == 0 for r in log)
+    sim.close()
