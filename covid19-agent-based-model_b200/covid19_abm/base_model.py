@@ -198,7 +198,10 @@ class Country:
         p = self.params
         size = df.shape[0]
         first_household = max(p.DISTRICT_ID_TO_NAME) + 1       # households are numbered after the districts
-        hh_names, hh_codes = np.unique(df['household_id'].values.astype(str), return_inverse=True)
+        # (factorize hashes each string once and sorts only the distinct names: the dict maps of the reference,
+        # base_model.py:577-611, are what dominates its load time at millions of agents)
+        hh_codes, hh_names = pd.factorize(df['household_id'].astype(str), sort=True)
+        hh_names = np.asarray(hh_names)
         p.HOUSEHOLD_ID_TO_NAME = dict(enumerate(hh_names.tolist(), first_household))
         p.HOUSEHOLD_NAME_TO_ID = {n: i for i, n in p.HOUSEHOLD_ID_TO_NAME.items()}
         if self.is_school_scenario:                             # schools after the households
@@ -214,13 +217,38 @@ class Country:
             p.LOCATION_ID_TO_NAME.update(p.SCHOOL_ID_TO_NAME)
         p.LOCATION_NAME_TO_ID = {n: i for i, n in p.LOCATION_ID_TO_NAME.items()}
 
+        def codes_of(column, names_by_id):
+            """ids of a string column whose names are those of `names_by_id` (id -> name)."""
+            names = [names_by_id[i] for i in range(len(names_by_id))]
+            codes = pd.Categorical(df[column], categories=names).codes.astype(np.int64)
+            if (codes < 0).any():                                # unknown name: let the reference-style map decide (NaN)
+                return np.array(df[column].map({n: i for i, n in names_by_id.items()}))
+            return codes
+
         self.person_ids = np.arange(size, dtype=int)
-        self.district_ids = np.array(df['district_id'].map(p.DISTRICT_NAME_TO_ID))
+        self.district_ids = codes_of('district_id', p.DISTRICT_ID_TO_NAME)
         self.household_ids = hh_codes.astype(np.int64) + first_household
         self.age = np.array(df['age'])
         self.sex = np.array(df['sex'].map(p.SEX_NAME_TO_ID))
-        self.economic_status_ids = np.array(df['economic_status'].map(p.ECON_STAT_NAME_TO_ID))
-        self.economic_activity_location_ids = np.array(df['economic_activity_location_id'].map(p.LOCATION_NAME_TO_ID))
+        self.economic_status_ids = codes_of('economic_status', p.ECON_STAT_ID_TO_NAME)
+        # the work / school place is almost always the person's own household or home district: compare names
+        # column-wise and send only the rest through the name -> id dictionary
+        place = df['economic_activity_location_id'].astype(str).values
+        own_household = place == df['household_id'].astype(str).values
+        own_district = ~own_household & (place == df['district_id'].astype(str).values)
+        loc = np.where(own_household, self.household_ids, np.where(own_district, self.district_ids, -1)).astype(np.int64)
+        # a name that is both a district and a household (mining camps) resolves to the household, as in the inverted
+        # dictionary of the reference (base_model.py:594-599)
+        both = set(p.DISTRICT_NAME_TO_ID).intersection(p.HOUSEHOLD_NAME_TO_ID)
+        rest = loc < 0
+        if both:
+            rest |= own_district & pd.Series(place).isin(both).values
+        if rest.any():
+            mapped = pd.Series(place[rest]).map(p.LOCATION_NAME_TO_ID).values
+            if np.isnan(mapped.astype(np.float64)).any():
+                loc = loc.astype(np.float64)
+            loc[rest] = mapped
+        self.economic_activity_location_ids = loc
         self.economic_status_ids_person_ids = {i: set(np.nonzero(self.economic_status_ids == i)[0])
                                                for i in p.ECON_STAT_ID_TO_NAME}
         self.economic_status_weekday_movement_probability = np.array(
