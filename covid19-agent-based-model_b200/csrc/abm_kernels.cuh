@@ -972,19 +972,28 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             __syncthreads();
             if (t == 0)
                 st_release_sys(reinterpret_cast<unsigned int*>(Wk.xchg[Wk.rank] + flag_words) + (gen & 1u) * T.P + L, gen);
-            if (t < Wk.n_ranks && t != Wk.rank) {
-                const unsigned int* flag = reinterpret_cast<const unsigned int*>(Wk.xchg[t] + flag_words) + (gen & 1u) * T.P + L;
-                int spins = 0;
-                while ((int)(ld_acquire_sys(flag) - gen) < 0) {
-                    if (++spins > (1 << 22)) { clk->xchg_error = 1; break; }     // a peer is gone: do not hang the GPU
-                    __nanosleep(64);
+            // warp g takes the peers g, g + 8, ...: its first lane waits for the peer's flag, then the warp reads the
+            // peer's row -- the peers are read side by side, one NVLink round trip for all of them
+            unsigned long long from_peers = 0ull;
+            for (int r = g; r < Wk.n_ranks; r += TABLE_THREADS / 32) {
+                if (r == Wk.rank) continue;
+                if (e == 0) {
+                    const unsigned int* flag = reinterpret_cast<const unsigned int*>(Wk.xchg[r] + flag_words) + (gen & 1u) * T.P + L;
+                    int spins = 0;
+                    while ((int)(ld_acquire_sys(flag) - gen) < 0) {
+                        if (++spins > (1 << 22)) { clk->xchg_error = 1; break; }     // a peer is gone: do not hang the GPU
+                        __nanosleep(64);
+                    }
                 }
+                __syncwarp();
+                if (e < 2 * A) from_peers += ld_relaxed_sys(Wk.xchg[r] + (size_t)(gen & 1u) * 2 * n + off);
             }
+            s_part[g][e] = from_peers;
             __syncthreads();
             if (t < 2 * A) {
                 unsigned long long total = s_row[t];
-                for (int r = 0; r < Wk.n_ranks; ++r)
-                    if (r != Wk.rank) total += ld_relaxed_sys(Wk.xchg[r] + (size_t)(gen & 1u) * 2 * n + off);
+#pragma unroll
+                for (int w = 0; w < TABLE_THREADS / 32; ++w) total += s_part[w][t];
                 Wk.acc_sum[off] = total;
                 s_row[t] = total;
             }
