@@ -514,9 +514,7 @@ __global__ void __launch_bounds__(THREADS)
 abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* __restrict__ clk, const uint32_t mode_rt) {
     __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
     __shared__ unsigned int s_acc[WARPS][2 * ABM_MAX_STATUS];   // per-warp home-pool pressure sums / head counts
-    __shared__ int s_tally[N_TALLY];
-    __shared__ int s_home[WARPS];
-    __shared__ unsigned int s_done;
+    __shared__ int s_tally_all[WARPS][N_TALLY];       // per-warp event tallies: a warp shares nothing with its CTA
 
     const uint32_t mode_static = MODE == RUNTIME_MODE ? (mode_rt & 0xFFFFu) : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -534,11 +532,10 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     uint32_t ix = 0;
     if (mode_static & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
 
-    if (tid < N_TALLY) s_tally[tid] = 0;
+    int* s_tally = s_tally_all[wid];
+    if (lane < N_TALLY) s_tally[lane] = 0;
     if (lane < 2 * ABM_MAX_STATUS) s_acc[wid][lane] = 0u;
-    if (lane == 0) s_home[wid] = L0;
-    if (tid == 0) s_done = 0u;
-    __syncthreads();
+    __syncwarp();
 
     uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
     uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
@@ -862,32 +859,20 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
         *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
     }
 
-    // ================================================================ flush of the per-CTA counters by the last warp to finish
-    __threadfence_block();
-    unsigned int done = 0;
-    if (lane == 0) done = atomicAdd(&s_done, 1u);
-    done = __shfl_sync(FULL, done, 0);
-    if (done != WARPS - 1) return;
-    __threadfence_block();
+    // ================================================================ flush of the warp's counters
+    __syncwarp();
+    const uint32_t rep = blockIdx.x * WARPS + wid;     // replica of the accumulators this warp adds to
     if (lane < N_TALLY) {
         const int v = s_tally[lane];
-        if (v) atomicAdd(Wk.tally + (size_t)(blockIdx.x & Wk.rep_mask) * N_TALLY + lane, (unsigned long long)(long long)v);
+        if (v) atomicAdd(Wk.tally + (size_t)(rep & Wk.rep_mask) * N_TALLY + lane, (unsigned long long)(long long)v);
     }
     if ((mode & M_DENSE_A) && !(mode & M_INCR) && lane < 2 * ABM_MAX_STATUS) {
-        // lanes 0..11: pressure sums, lanes 12..23: head counts; consecutive warps of one home district are merged
+        // lanes 0..11: pressure sums, lanes 12..23: head counts of the warp's home district
         const int b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
-        unsigned long long* dst = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A);
-        unsigned long long sum = 0ull;
-        int home = s_home[0];
-        for (int w = 0; w < WARPS; ++w) {
-            const int hw = s_home[w];
-            if (hw != home) {
-                if (sum && b < A) atomicAdd(dst + (size_t)home * A + b, sum);
-                sum = 0ull; home = hw;
-            }
-            sum += s_acc[w][lane];
-        }
-        if (sum && b < A) atomicAdd(dst + (size_t)home * A + b, sum);
+        const unsigned int v = acc_w[lane];
+        if (v && b < A)
+            atomicAdd(acc_k + (size_t)(rep & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A) + (size_t)L0 * A + b,
+                      (unsigned long long)v);
     }
 }
 
