@@ -18,7 +18,7 @@
 // households of a single home district and that slot offset o of a sub-tile is canonical agent id
 // base + o with base a multiple of 4, so (a) the household hazard is a warp-local segmented sum,
 // (b) the home district is a per-warp scalar and (c) one Philox4x32 block serves the four agents of a
-// lane.  Warps never wait for each other: per-CTA counters are flushed by whichever warp finishes last.
+// lane.  Warps never wait for each other: every warp keeps its own event tallies and accumulator row and flushes them itself.
 // The kernel is instruction-issue bound, not HBM bound (profiles/), so the code below is organised to
 // issue few instructions: flag fields that are tested together are adjacent, work that only a few agents
 // need (disease-course sampling, due transitions, travellers) runs in "funnel" loops -- every lane keeps
@@ -80,7 +80,7 @@ enum { CUM_CONTAGIOUS = 0, CUM_INFECTED, CUM_HOSPITALIZED, CUM_CRITICAL, CUM_DIE
        POST_EXPOSED, POST_CONTAGIOUS, POST_HOSPITALIZED, POST_CRITICAL, N_TALLY };
 
 #ifndef ABM_THREADS
-#define ABM_THREADS 128          // threads per CTA of the sub-step kernel: one warp per sub-tile, ABM_THREADS / 32 sub-tiles per CTA
+#define ABM_THREADS 256          // threads per CTA of the sub-step kernel: one warp per sub-tile, ABM_THREADS / 32 sub-tiles per CTA
 #endif
 constexpr int THREADS = ABM_THREADS;
 constexpr int WARPS = THREADS / 32;
