@@ -525,12 +525,14 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     const uint32_t slot0 = sub * SUB + lane * PER_LANE;
     const int A = T.A;
 
-    const uint4 f4 = *reinterpret_cast<const uint4*>(G.flags + slot0);
-    const uint4 a4 = *reinterpret_cast<const uint4*>(G.aux + slot0);
+    // streaming loads / stores (evict-first): the hot words are touched once per launch and must not push the small
+    // tables every warp re-reads out of L1
+    const uint4 f4 = __ldcs(reinterpret_cast<const uint4*>(G.flags + slot0));
+    const uint4 a4 = __ldcs(reinterpret_cast<const uint4*>(G.aux + slot0));
     // household index of each slot within the sub-tile (static, one byte per slot): issued with the hot
     // words so the household phase does not wait for a dependent DRAM round trip
     uint32_t ix = 0;
-    if (mode_static & M_INFECT) ix = __ldg(G.hh_index + (slot0 >> 2));
+    if (mode_static & M_INFECT) ix = __ldcs(G.hh_index + (slot0 >> 2));
 
     int* s_tally = s_tally_all[wid];
     if (lane < N_TALLY) s_tally[lane] = 0;
@@ -701,7 +703,7 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
 #undef ABM_BACK_HOME
         }
         if (mode & M_GO_OUT) {                                                          // :304-340
-            const uint2 mc = *reinterpret_cast<const uint2*>(G.move_class + slot0);
+            const uint2 mc = __ldcs(reinterpret_cast<const uint2*>(G.move_class + slot0));
             const uint32_t* thr_col = T.move_thr + ((mode & M_WEEKDAY) ? 0 : 2);
             const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
             const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
@@ -855,8 +857,8 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
 
     // ================================================================ write back what changed
     if (dirty) {
-        *reinterpret_cast<uint4*>(G.flags + slot0) = make_uint4(f0, f1, f2, f3);
-        *reinterpret_cast<uint4*>(G.aux + slot0) = make_uint4(a0, a1, a2, a3);
+        __stcs(reinterpret_cast<uint4*>(G.flags + slot0), make_uint4(f0, f1, f2, f3));
+        __stcs(reinterpret_cast<uint4*>(G.aux + slot0), make_uint4(a0, a1, a2, a3));
     }
 
     // ================================================================ flush of the warp's counters
