@@ -336,11 +336,11 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
         atomicAdd(tally + CUM_ASYM, (TallyT)1);
     }
     atomicAdd(tally + PRE_EXPOSED, (TallyT)1);
-    G.t_infected[slot] = now_inf;                                                           // :851
-    G.t_contagious[slot] = t_c;
-    G.t_onset[slot] = t_o;
-    G.t_recovered[slot] = t_r;
-    G.inf_at[slot] = (loc_of(f) << 16) | cur;                                               // :846-847
+    __stcs(G.t_infected + slot, now_inf);                                                   // :851
+    __stcs(G.t_contagious + slot, t_c);
+    __stcs(G.t_onset + slot, t_o);
+    __stcs(G.t_recovered + slot, t_r);
+    __stcs(G.inf_at + slot, (loc_of(f) << 16) | cur);                                       // :846-847
     f &= ~(F_EPI_MASK | F_SYMPT | F_ASYMPT | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
     f |= EPI_I | (sym ? F_SYMPT : F_ASYMPT) | out;                                          // :850
     // earliest scheduled event: the one with the smallest date (fire_index is monotone)
@@ -373,7 +373,7 @@ struct DeltaSink {          // where incremental sub-steps send their table chan
 __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
                                                      int32_t now, int* s_tally, const DeltaSink* sink = nullptr) {
     const uint32_t f_before = f;
-    const int32_t t_c = G.t_contagious[slot], t_o = G.t_onset[slot], t_r = G.t_recovered[slot];
+    const int32_t t_c = __ldcs(G.t_contagious + slot), t_o = __ldcs(G.t_onset + slot), t_r = __ldcs(G.t_recovered + slot);
     const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
     const int32_t t_cs = (f & F_OUT_C) ? t_o + 13 * DAY : T_NEVER;  // hospital end = critical start (base_model.py:953)
     const int32_t t_d = (f & F_OUT_D) ? t_o + 21 * DAY : T_NEVER;   // params.py:177 (== end of critical care when critical)
@@ -546,10 +546,10 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     // trip overlaps the infection and transition phases instead of stalling the movement phase
     int32_t tr0 = T_NEVER, tr1 = T_NEVER, tr2 = T_NEVER, tr3 = T_NEVER;
     if (mode_static & (M_GO_OUT | M_GO_HOME)) {
-        if (f0 & F_AWAY) tr0 = G.t_return[slot0 + 0];
-        if (f1 & F_AWAY) tr1 = G.t_return[slot0 + 1];
-        if (f2 & F_AWAY) tr2 = G.t_return[slot0 + 2];
-        if (f3 & F_AWAY) tr3 = G.t_return[slot0 + 3];
+        if (f0 & F_AWAY) tr0 = __ldcs(G.t_return + slot0 + 0);
+        if (f1 & F_AWAY) tr1 = __ldcs(G.t_return + slot0 + 1);
+        if (f2 & F_AWAY) tr2 = __ldcs(G.t_return + slot0 + 2);
+        if (f3 & F_AWAY) tr3 = __ldcs(G.t_return + slot0 + 3);
     }
     uint32_t* hz = s_hz[wid];
     unsigned int* acc_w = s_acc[wid];
