@@ -482,19 +482,6 @@ constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
             __VA_ARGS__                                                              \
         }                                                                            \
     }
-// Same, without the warp votes: a plain divergent loop (bodies without warp collectives); lanes leave as
-// soon as their own mask is empty and the warp reconverges behind the loop.
-#define ABM_LANE_LOOP_RW(mask, ...)                                                  \
-    while (mask) {                                                                   \
-        const int J = __ffs(mask) - 1;                                               \
-        (mask) &= (mask) - 1u;                                                       \
-        uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));              \
-        uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));              \
-        __VA_ARGS__                                                                  \
-        if (J == 0) { f0 = fj; a0 = aj; } else if (J == 1) { f1 = fj; a1 = aj; }     \
-        else if (J == 2) { f2 = fj; a2 = aj; } else { f3 = fj; a3 = aj; }            \
-        dirty = true;                                                                \
-    }
 #define ABM_FUNNEL_RW(mask, ...)                                                     \
     while (__any_sync(FULL, (mask) != 0u)) {                                         \
         if (mask) {                                                                  \
@@ -741,17 +728,24 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_GO_OUT(f3, XO.w, 8u)
 #undef ABM_GO_OUT
             // travellers: back in the home district when the stay is over (:342-360), then like everybody else
-            ABM_LANE_LOOP_RW(away, {
-                bool out_again = false;
-                if ((J == 0 ? tr0 : (J == 1 ? tr1 : (J == 2 ? tr2 : tr3))) < s.now) {
-                    aj = (aj & 0xFFFF0000u) | (uint32_t)L0;
-                    fj &= ~F_AWAY;
-                    const uint32_t u = word_of(XO, J) >> 1;
-                    out_again = (fj & F_DMOVER) && !(u >= od_lo && u < od_hi);
-                }
-                if (out_again) leave |= 1u << J;
-                else fj = set_loc(fj, econ_loc(fj));                                    // :331-339, :346-352
-            })
+#define ABM_TRAVELLER(fj, aj, trj, xo, bit)                                                          \
+            if (away & (bit)) {                                                                      \
+                bool out_again = false;                                                              \
+                if ((trj) < s.now) {                                                                 \
+                    aj = ((aj) & 0xFFFF0000u) | (uint32_t)L0;                                        \
+                    fj &= ~F_AWAY;                                                                   \
+                    const uint32_t u = (xo) >> 1;                                                    \
+                    out_again = ((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi);                     \
+                }                                                                                    \
+                if (out_again) leave |= (bit);                                                       \
+                else fj = set_loc(fj, econ_loc(fj));                                    /* :331-339, :346-352 */ \
+                dirty = true;                                                                        \
+            }
+            ABM_TRAVELLER(f0, a0, tr0, XO.x, 1u)
+            ABM_TRAVELLER(f1, a1, tr1, XO.y, 2u)
+            ABM_TRAVELLER(f2, a2, tr2, XO.z, 4u)
+            ABM_TRAVELLER(f3, a3, tr3, XO.w, 8u)
+#undef ABM_TRAVELLER
             // district movers whose draw is not in the stay-home interval: find the destination (:366-441)
             ABM_FUNNEL_RW(leave, {
                 const uint32_t dest = od_destination(od_row, T.D, word_of(XO, J) >> 1);
