@@ -22,6 +22,11 @@ def load_reference(case):
 def build_world(root, ref):
     spec = synth.make_spec(n_districts=ref['n_districts'], R0=ref['R0'], seed=POP_SEED, start_datetime=datetime(2020, 9, 1, 0))
     pop = synth.make_population(ref['n_agents'], spec, seed=POP_SEED, scenario_flags=True)
+    if ref['case'] in ('selective_lockdown_100k', 'open_manufacturing_schools_100k'):
+        # the census columns the sector / school scenarios read, exactly as tests/golden/make_ref_ensemble.py adds them
+        names = np.array(synth.district_names(ref['n_districts']))
+        pop.extras['manufacturing_workers'] = np.where(pop.extras['manufacturing_workers'] == 1, 1.0, np.nan)
+        pop.extras['school_id_district'] = np.where(pop.extras['school_goers'] == 1, names[pop.district], '')
     cases = synth.seed_case_counts(pop, spec, seed=POP_SEED)
     synth.write_data_dir(root, spec, pop, seed_cases=cases, seed=0)
     os.environ['COVID19_ABM_DATA_DIR'] = root

@@ -26,8 +26,22 @@ CASES = {
     # name: (scenario class, n_agents, n_districts, days, infect_num, members, R0)
     'unmitigated_100k': ('UnmitigatedScenario', 100_000, 60, 45, 200, 64, 1.9),
     'lockdown_100k': ('ContinuedLockdownScenario', 100_000, 60, 45, 200, 32, 1.9),
+    # BASELINE.json configs[2]: selective lockdown of the ten high-mobility districts
+    'selective_lockdown_100k': ('LockdownGreatestMobilityScenario', 100_000, 60, 45, 200, 32, 1.9),
+    # BASELINE.json configs[3]: continued lockdown with schools and manufacturing re-opened
+    'open_manufacturing_schools_100k': ('OpenManufacturingAndSchoolsScenario', 100_000, 60, 45, 200, 32, 1.9),
 }
 POP_SEED = 2020
+
+
+def scenario_columns(pop, n_districts):
+    """Census columns the sector / school scenarios read (scenario_models.py:329, 349): manufacturing workers are the
+    non-null rows, school goers carry the district of their school.  Same function on both sides of the comparison."""
+    from abm_b200 import synth
+    names = np.array(synth.district_names(n_districts))
+    pop.extras['manufacturing_workers'] = np.where(pop.extras['manufacturing_workers'] == 1, 1.0, np.nan)
+    pop.extras['school_id_district'] = np.where(pop.extras['school_goers'] == 1, names[pop.district], '')
+    return pop
 
 
 def member(args):
@@ -38,6 +52,8 @@ def member(args):
     start = datetime(2020, 9, 1, 0)
     spec = synth.make_spec(n_districts=D, R0=R0, seed=POP_SEED, start_datetime=start)
     pop = synth.make_population(n_agents, spec, seed=POP_SEED, scenario_flags=True)
+    if case in ('selective_lockdown_100k', 'open_manufacturing_schools_100k'):
+        pop = scenario_columns(pop, D)
     cases = synth.seed_case_counts(pop, spec, seed=POP_SEED)
     world = rh.RefWorld(spec, pop, seed_cases=cases)
     log_file = os.path.join(world.tmp, 'logs', 'model.log')
