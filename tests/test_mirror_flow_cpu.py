@@ -45,3 +45,15 @@ def test_real_time_cannot_be_set_while_running(tmp_path, fake_engine):
     groups = m.get_location_person_ids()
     assert sum(len(v) for v in groups.values()) == m.person_ids.shape[0]
     assert m.scheduler.get_active_ids().shape[0] > 0
+
+
+@pytest.mark.parametrize('scenario', ['DynamicPhase1GovernmentOpenSchoolsScenario', 'Phase1GovernmentOpenSchoolsScenario'])
+def test_other_school_scenarios_run(tmp_path, fake_engine, scenario):
+    """The monthly clock hooks of the two other government school scenarios (base_model.py:809-834): the dynamic one
+    asks for the safe / unsafe districts on the 1st of the month (quirk Q10: it gets rates back, so nobody matches)."""
+    start = datetime(2020, 12, 30, 0) if scenario.startswith('Phase1') else datetime(2020, 9, 29, 0)
+    m, ora, rows = dropin_flow.run_flow(tmp_path, scenario, days=4, start=start, n_agents=6000, school_columns=True)
+    safe, unsafe = m.get_safe_and_unsafe_districts()
+    assert safe.shape[0] + unsafe.shape[0] == 60 and safe.max() <= unsafe.min() if unsafe.size else True
+    if scenario.startswith('Phase1'):
+        assert m.active_school_phases[:3] == [1, 2, 4]            # appended on every sub-step of 2021-01-01 (Q10)
