@@ -143,7 +143,7 @@ def run_reference_arm(a):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
+    procs = max(1, min(cores, 64))
     n = a.cpu_agents
     warm = min(a.warmup, 1)
     days = max(1, min(a.steps, 3))
