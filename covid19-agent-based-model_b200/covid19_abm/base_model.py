@@ -522,11 +522,12 @@ class Country:
 
     # ------------------------------------------------------------------ read-back of the dynamic vectors
     def _to_datetimes(self, ticks):
+        """int32 minute ticks -> object array of `datetime` (`datetime.max` = never), as the reference stores dates."""
         out = np.full(ticks.shape[0], datetime.max, dtype=object)
         hit = np.nonzero(ticks != T_NEVER)[0]
         if hit.size:
-            t0 = self._spec_obj.start_datetime
-            out[hit] = [t0 + timedelta(minutes=int(t)) for t in ticks[hit]]
+            t0 = np.datetime64(self._spec_obj.start_datetime, 'us')
+            out[hit] = (t0 + ticks[hit].astype('timedelta64[m]')).astype(object)      # converted in C, not in a Python loop
         return out
 
     def _read_back(self):
