@@ -103,3 +103,35 @@ def test_run_scenario_driver(tmp_path):
         by_hand.close(); model.close()
     finally:
         scenario_models.UnmitigatedScenario.philox_seed = None
+
+
+def test_dropin_at_scale_equals_engine_level_run(tmp_path):
+    """1 M agents through the drop-in (shuffled census, lockdown hooks, seeding, 20 days in one call) give the day log
+    and the per-person state of an engine-level Simulation fed the same canonical population, spec, seeds and key."""
+    from abm_b200 import tables
+    from abm_b200.engine import COUNTER_NAMES, Simulation
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    dropin_flow.build_world(root, n_agents=1_000_000)
+    m = dropin_flow.make_model('ContinuedLockdownScenario', datetime(2020, 9, 1, 0), log_file=str(tmp_path / 'm.log'))
+    seeded = np.sort(m._canon_of_person[np.nonzero(m.epidemic_state > 0)[0]])
+    m.run_days(20)
+    sim = Simulation(m._spec_obj, m._pop, seed=m._philox_seed, tables=tables.build_tables(m._spec_obj), max_days=30)
+    sim.seed_infections(seeded)
+    sim.step(6 * 20)
+    rows = dropin_flow.read_log(str(tmp_path / 'm.log'))
+    want = sim.log_dicts()
+    assert len(rows) == len(want) == 20
+    for g, w in zip(rows, want):
+        assert g['date'] == w['date']
+        for name in COUNTER_NAMES:
+            assert g[name] == w[name], (name, g['date'])
+    st = sim.state()
+    cp = m._canon_of_person
+    assert np.array_equal(m.epidemic_state.astype(np.int64), st['epidemic_state'].astype(np.int64)[cp])
+    assert np.array_equal(m.current_district_ids, st['current_district_ids'][cp])
+    assert np.array_equal(m.event_ticks('date_recovered'), st['date_recovered'][cp])
+    n = m.person_ids.shape[0]
+    assert n == 1_000_000 and rows[-1]['infected_count'] > 300
+    assert m.active_infections() == int(((st['epidemic_state'] >= 1) & (st['epidemic_state'] < 3)).sum())
+    sim.close(); m.close()
