@@ -86,6 +86,9 @@ def test_run_scenario_driver(tmp_path):
         assert len(logs) == 1 and len(dumps) == 1
         rows = dropin_flow.read_log(logs[0])
         assert len(rows) == 10 and rows[0]['date'] == '2021-05-22T08:00:00' and rows[-1]['infected_count'] > 300
+        from covid19_abm import data_plotting                      # the notebooks' reader of that file (§8 f1)
+        df = data_plotting.load_model_logs_df(logs[0])
+        assert len(df) == 10 and int(df['new_cases'].sum()) == rows[-1]['infected_count']
         with open(dumps[0], 'rb') as fl:
             again = pickle.load(fl)
         assert again._sim is None and np.array_equal(again.epidemic_state, model.epidemic_state)
