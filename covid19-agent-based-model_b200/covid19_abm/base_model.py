@@ -160,6 +160,7 @@ class Country:
         self._log_rows_due = 0
         self._log_rows_written = 0
         self._restore = None
+        self._status_person_ids = None
 
         for name in ('person_ids', 'district_ids', 'household_ids', 'age', 'sex', 'economic_status_ids',
                      'economic_activity_location_ids', 'left_district_at', 'economic_status_weekday_movement_probability',
@@ -218,18 +219,30 @@ class Country:
         p.LOCATION_NAME_TO_ID = {n: i for i, n in p.LOCATION_ID_TO_NAME.items()}
 
         def codes_of(column, names_by_id):
-            """ids of a string column whose names are those of `names_by_id` (id -> name)."""
-            names = [names_by_id[i] for i in range(len(names_by_id))]
-            codes = pd.Categorical(df[column], categories=names).codes.astype(np.int64)
-            if (codes < 0).any():                                # unknown name: let the reference-style map decide (NaN)
-                return np.array(df[column].map({n: i for i, n in names_by_id.items()}))
-            return codes
+            """ids of a string column whose names are those of `names_by_id` (id -> name): the column is hashed once
+            (factorize) and only its few distinct names go through the dictionary."""
+            codes, names = pd.factorize(df[column])
+            id_of = {n: i for i, n in names_by_id.items()}
+            lut = np.array([id_of.get(n, -1) for n in names] + [-1], dtype=np.int64)     # last entry: missing value
+            ids = lut[codes]
+            if (ids < 0).any():                                  # unknown name: let the reference-style map decide (NaN)
+                return np.array(df[column].map(id_of))
+            return ids
+
+        def by_status(mapping):
+            """Per-agent value of a {status name: value} table (`df['economic_status'].map(mapping)` in the reference,
+            base_model.py:617-620), looked up through the status ids."""
+            ids = self.economic_status_ids
+            if ids.dtype.kind != 'i' or any(name not in mapping for name in p.ECON_STAT_NAME_TO_ID):
+                return np.array(df['economic_status'].map(mapping))
+            table = np.array([mapping[p.ECON_STAT_ID_TO_NAME[i]] for i in range(len(p.ECON_STAT_ID_TO_NAME))])
+            return table[ids]
 
         self.person_ids = np.arange(size, dtype=int)
         self.district_ids = codes_of('district_id', p.DISTRICT_ID_TO_NAME)
         self.household_ids = hh_codes.astype(np.int64) + first_household
         self.age = np.array(df['age'])
-        self.sex = np.array(df['sex'].map(p.SEX_NAME_TO_ID))
+        self.sex = codes_of('sex', p.SEX_ID_TO_NAME)
         self.economic_status_ids = codes_of('economic_status', p.ECON_STAT_ID_TO_NAME)
         # the work / school place is almost always the person's own household or home district: compare names
         # column-wise and send only the rest through the name -> id dictionary
@@ -249,18 +262,24 @@ class Country:
                 loc = loc.astype(np.float64)
             loc[rest] = mapped
         self.economic_activity_location_ids = loc
-        self.economic_status_ids_person_ids = {i: set(np.nonzero(self.economic_status_ids == i)[0])
-                                               for i in p.ECON_STAT_ID_TO_NAME}
-        self.economic_status_weekday_movement_probability = np.array(
-            df['economic_status'].map(p.ECONOMIC_STATUS_WEEKDAY_MOVEMENT_PROBABILITY))
-        self.economic_status_other_day_movement_probability = np.array(
-            df['economic_status'].map(p.ECONOMIC_STATUS_OTHER_DAY_MOVEMENT_PROBABILITY))
+        self._status_person_ids = None                          # built on first use (economic_status_ids_person_ids)
+        self.economic_status_weekday_movement_probability = by_status(p.ECONOMIC_STATUS_WEEKDAY_MOVEMENT_PROBABILITY)
+        self.economic_status_other_day_movement_probability = by_status(p.ECONOMIC_STATUS_OTHER_DAY_MOVEMENT_PROBABILITY)
         self._host['mild_symptom_movement_probability'] = np.ones(shape=size)
         self._host['current_location_ids'] = np.array(self.household_ids)
         self._host['current_district_ids'] = np.array(self.district_ids)
         self.left_district_at = np.full(shape=size, fill_value=datetime.max)
         self._host['return_district_at'] = np.full(shape=size, fill_value=datetime.max)
         self.district_mover = self.DISTRICT_MOVER_TRUE * self._may_travel(self.age >= p.DISTRICT_MOVEMENT_ALLOWED_AGE)
+
+    @property
+    def economic_status_ids_person_ids(self):
+        """{status id: set of person ids} (base_model.py:613).  Only the reference's explicit contact sampler reads it
+        (:84); here it is built when somebody asks, not at load time (python sets of every person id)."""
+        if self._status_person_ids is None and self.economic_status_ids is not None:
+            self._status_person_ids = {i: set(np.nonzero(self.economic_status_ids == i)[0])
+                                       for i in self.params.ECON_STAT_ID_TO_NAME}
+        return self._status_person_ids
 
     def _may_travel(self, age_ok):
         moving = [self.params.ECON_STAT_NAME_TO_ID[s] for s in self.params.DISTRICT_MOVING_ECONOMIC_STATUS
@@ -461,11 +480,17 @@ class Country:
         from abm_b200 import tables
         from abm_b200.engine import Simulation
         n = self.person_ids.shape[0]
-        order = np.lexsort((self.household_ids, self.district_ids))        # canonical order: (home district, household)
+        # canonical order: (home district, household), ties in person order -- one stable sort of a combined key
+        span = int(self.household_ids.max()) + 1
+        if int(self.district_ids.max()) < (2 ** 62) // span:
+            order = np.argsort(self.district_ids.astype(np.int64) * span + self.household_ids, kind='stable')
+        else:
+            order = np.lexsort((self.household_ids, self.district_ids))
         hh = self.household_ids[order]
         new_hh = np.r_[True, hh[1:] != hh[:-1]]
         dense = np.cumsum(new_hh) - 1
-        if int(dense[-1]) + 1 != np.unique(self.household_ids).shape[0]:
+        lowest = int(self.household_ids.min())
+        if int(dense[-1]) + 1 != int(np.count_nonzero(np.bincount(self.household_ids - lowest))):
             raise NotImplementedError('a household has members with different home districts: the household-aligned device '
                                       'layout cannot hold it')
         self._order = order
@@ -673,10 +698,12 @@ class Country:
             d['_host'] = {name: self._dynamic_vector(name) for name in _DYNAMIC}
         d['_sim'] = None
         d['_fresh'] = {}
+        d['_status_person_ids'] = None                           # derived; rebuilt on demand
         return d
 
     def __setstate__(self, d):
         self.__dict__.update(d)
+        self.__dict__.setdefault('_status_person_ids', None)
 
     def close(self):
         if self._sim is not None:
