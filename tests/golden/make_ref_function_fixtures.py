@@ -154,6 +154,11 @@ def run_case(name, scenario, n_agents, n_districts, n_steps, seed, philox_seed, 
         pop.move_prob_weekday = np.asarray(model.economic_status_weekday_movement_probability, dtype=np.float64).copy()
         pop.move_prob_other = np.asarray(model.economic_status_other_day_movement_probability, dtype=np.float64).copy()
         assert np.array_equal(np.asarray(model.district_ids), pop.district)
+        # where the scenario hook sends people at 08:00 (IsolateVulnerable keeps the elderly in their household)
+        econ = np.asarray(model.economic_activity_location_ids).astype(np.int64)
+        at_household = econ == np.asarray(model.household_ids)
+        assert (at_household | (econ == np.asarray(model.district_ids))).all()
+        pop.econ_kind = np.where(at_household, rh.C.EKIND_HOUSEHOLD, rh.C.EKIND_HOME_DISTRICT).astype(pop.econ_kind.dtype)
         assert np.array_equal(np.asarray(model.household_ids), pop.household + n_districts)
         tab = tables.build_tables(spec)
         par = dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob)
@@ -244,3 +249,9 @@ if __name__ == '__main__':
              seed=12, philox_seed=0x5EED0002, snapshot_every=60, infect_num=50)
     run_case('lockdown', 'ContinuedLockdownScenario', n_agents=2500, n_districts=5, n_steps=6 * 30,
              seed=13, philox_seed=0x5EED0003, snapshot_every=60, infect_num=50)
+    run_case('handwashing_risk', 'HandWashingRiskScenario', n_agents=2500, n_districts=5, n_steps=6 * 30,
+             seed=14, philox_seed=0x5EED0004, snapshot_every=60, infect_num=50)
+    run_case('isolate_vulnerable', 'IsolateVulnerableScenario', n_agents=2500, n_districts=5, n_steps=6 * 30,
+             seed=15, philox_seed=0x5EED0005, snapshot_every=60, infect_num=50)
+    run_case('block_mobility', 'BlockGreatestMobilityScenario', n_agents=2500, n_districts=12, n_steps=6 * 30,
+             seed=16, philox_seed=0x5EED0006, snapshot_every=60, infect_num=50)

@@ -6,7 +6,7 @@ from oracle.abm_oracle import OracleModel
 from abm_b200 import tables
 from util import assert_state_equal, load_fixture, oracle_params
 
-CASES = ['unmitigated', 'isolate_symptomatic', 'lockdown']
+CASES = ['unmitigated', 'isolate_symptomatic', 'lockdown', 'handwashing_risk', 'isolate_vulnerable', 'block_mobility']
 
 
 @pytest.mark.parametrize('name', CASES)
