@@ -160,7 +160,8 @@ def pick_seeds(pop: Population, spec: ModelSpec, infect_num=None, seed=0, cases=
 
 
 # ---------------------------------------------------------------------------------------------------- data directory
-def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=None, school_columns=False):
+def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=None, school_columns=False,
+                            mining_columns=False, mining_share=0.04):
     """Census-style DataFrame with the columns `Country.load_agents` reads.
     Zero-padded household names keep the string sort of base_model.py:577-581 equal to the numeric order."""
     import pandas as pd
@@ -188,6 +189,12 @@ def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=N
         df['school_id'] = np.where(pupil, np.char.add(np.char.add('s_', d_names), np.char.add('_', school_no)), '')
         df['school_id_district'] = np.where(pupil, d_names, '')
         df['phase'] = np.where(pupil, 1 + (pop.age % 5), 0)
+    if mining_columns:
+        # a share of the adult workers of every fifth district live and work in that district's mining camp (census
+        # column `mining_district_id` = 'mining_<district>', scenario_models.py:232-236; census notebook cells 41, 44)
+        miner = (pop.district % 5 == 2) & (pop.status >= 3) & (pop.status <= 6) & (pop.age >= 18) & (
+            np.random.default_rng(seed + 911).random(pop.n) < mining_share)
+        df['mining_district_id'] = np.where(miner, np.char.add('mining_', d_names), '')
     return df
 
 
@@ -249,7 +256,7 @@ def write_interaction_workbook(path, status_names, matrix, sizes):
 
 
 def write_data_dir(root, spec: ModelSpec, pop: Population, seed_cases=None, sample_tag=100, seed=0,
-                   lockdown_interaction_scale=0.5, school_columns=False):
+                   lockdown_interaction_scale=0.5, school_columns=False, mining_columns=False, mining_share=0.04):
     """Synthesise the data directory `run_scenario` expects (the real inputs are private): census pickle, OD csv,
     stay pickle, line list, intra-district mobility rates, interaction workbooks (normal / lockdown / sensitivity)
     and the risk csv.  Point COVID19_ABM_DATA_DIR at `root` to use it.  Returns the census file name."""
@@ -292,5 +299,6 @@ def write_data_dir(root, spec: ModelSpec, pop: Population, seed_cases=None, samp
                   'severe_covid_risk_improved_1': severe * 0.9, 'severe_covid_risk_improved_2': severe * 0.8}).to_csv(
         os.path.join(root, 'preprocessed', 'risk', 'hw_and_severe_disease_risk.csv'), index=False)
     census = os.path.join(root, 'preprocessed', 'census', f'zimbabwe_expanded_census_consolidated_{sample_tag}pct.pickle')
-    population_to_dataframe(pop, D, seed, spec.status_names, school_columns=school_columns).to_pickle(census)
+    population_to_dataframe(pop, D, seed, spec.status_names, school_columns=school_columns,
+                            mining_columns=mining_columns, mining_share=mining_share).to_pickle(census)
     return census

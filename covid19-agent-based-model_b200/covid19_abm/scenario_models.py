@@ -1,4 +1,4 @@
-"""The 18 scenario classes and `run_scenario` of the reference
+"""The 20 scenario classes and `run_scenario` of the reference
 (/root/reference/src/covid19_abm/scenario_models.py:9-500), on the GPU-backed `Country`.
 
 A scenario = a `ParamsConfig.scenario_*()` mutator applied in the constructor + two hooks around

@@ -15,11 +15,13 @@ from util import STATE_KEYS
 T_NEVER = 2 ** 31 - 1
 
 
-def build_world(root, n_agents=20_000, n_districts=60, seed=7, R0=2.6, school_columns=False, shuffle=True):
+def build_world(root, n_agents=20_000, n_districts=60, seed=7, R0=2.6, school_columns=False, shuffle=True,
+                mining_columns=False, mining_share=0.04):
     spec = synth.make_spec(n_districts=n_districts, R0=R0, seed=seed, start_datetime=datetime(2020, 9, 1, 0))
     pop = synth.make_population(n_agents, spec, seed=seed, scenario_flags=True)
     pop.extras['manufacturing_workers'] = np.where(pop.extras['manufacturing_workers'] == 1, 1.0, np.nan)
-    census = synth.write_data_dir(root, spec, pop, seed=seed, school_columns=school_columns)
+    census = synth.write_data_dir(root, spec, pop, seed=seed, school_columns=school_columns, mining_columns=mining_columns,
+                                  mining_share=mining_share)
     if shuffle:      # person order != canonical (district, household) order, as in a real census extract
         import pandas as pd
         df = pd.read_pickle(census)

@@ -57,3 +57,21 @@ def test_other_school_scenarios_run(tmp_path, fake_engine, scenario):
     assert safe.shape[0] + unsafe.shape[0] == 60 and safe.max() <= unsafe.min() if unsafe.size else True
     if scenario.startswith('Phase1'):
         assert m.active_school_phases[:3] == [1, 2, 4]            # appended on every sub-step of 2021-01-01 (Q10)
+
+
+def test_open_mining_flow_with_camps(tmp_path, fake_engine):
+    """OpenMiningScenario (scenario_models.py:224-246): miners live and work in the camp of their district -- one
+    household of tens of people (beyond the 32-member household tile), exempt from the lockdown, never travelling."""
+    m, ora, rows = dropin_flow.run_flow(tmp_path, 'OpenMiningScenario', days=8, n_agents=12000, mining_columns=True,
+                                        mining_share=0.6)
+    names = m.params.HOUSEHOLD_ID_TO_NAME
+    camp_ids = [i for i, n in names.items() if n.startswith('mining_')]
+    assert len(camp_ids) == 12 and min(camp_ids) == max(names) - 11           # sorted after every 'h_...' household
+    in_camp = np.isin(m.household_ids, camp_ids)
+    size = np.bincount(m.household_ids[in_camp] - min(camp_ids))
+    assert size.max() > 32 and rows[-1]['infected_count'] > 100
+    assert not m.district_mover[in_camp].any()
+    assert np.array_equal(m.economic_activity_location_ids[in_camp], m.household_ids[in_camp])
+    # miners keep their full weekday movement probability; their locked-down neighbours do not
+    assert (m.economic_status_weekday_movement_probability[in_camp] == 1.0).all()
+    assert m.economic_status_weekday_movement_probability[~in_camp].mean() < 0.9

@@ -98,16 +98,18 @@ def test_every_reference_scenario_mutator_exists(world):
     assert p.VULNERABLE_LOCATION == -N_DISTRICTS
 
 
-@pytest.mark.parametrize('name', SCENARIOS)
-def test_load_agents_host_vectors_match_reference(world, name):
+def load_scenario(name, np_seed):
     from covid19_abm import scenario_models
-    ref = world['ref']
-    np.random.seed(NP_SEED)
+    np.random.seed(np_seed)
     p = make_params()
     m = getattr(scenario_models, name)(p, model_log_file=None, individual_log_file=None)
     p.SIMULATION_START_DATE = datetime(2020, 9, 1, 0)
     m.scheduler.real_time = p.SIMULATION_START_DATE
     m.load_agents(p.data_file_name, size=None, infect_num=None)
+    return m, p
+
+
+def check_host_vectors(ref, name, m, p):
     pre = name + '/'
     assert np.array_equal(m.district_mover, ref[pre + 'district_mover'])
     assert np.array_equal(m.economic_status_weekday_movement_probability, ref[pre + 'move_weekday'])
@@ -130,6 +132,12 @@ def test_load_agents_host_vectors_match_reference(world, name):
     # the model pickles before any device exists (scenario_models.py:497-500)
     again = pickle.loads(pickle.dumps(m))
     assert np.array_equal(again.district_mover, m.district_mover) and again.params.SCENARIO == p.SCENARIO
+
+
+@pytest.mark.parametrize('name', SCENARIOS)
+def test_load_agents_host_vectors_match_reference(world, name):
+    m, p = load_scenario(name, NP_SEED)
+    check_host_vectors(world['ref'], name, m, p)
 
 
 def test_step_without_gpu_fails_loudly(world):
