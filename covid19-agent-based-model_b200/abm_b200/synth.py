@@ -160,6 +160,27 @@ def pick_seeds(pop: Population, spec: ModelSpec, infect_num=None, seed=0, cases=
 
 
 # ---------------------------------------------------------------------------------------------------- data directory
+def mining_camp_column(pop: Population, n_districts, seed=0, share=0.04):
+    """Census column `mining_district_id` (scenario_models.py:232-236; census notebook cells 41, 44): a share of the
+    adult workers of every fifth district live and work in that district's mining camp, 'mining_<district>'; '' for
+    everybody else."""
+    d_names = np.array(district_names(n_districts))[pop.district]
+    miner = (pop.district % 5 == 2) & (pop.status >= 3) & (pop.status <= 6) & (pop.age >= 18) & (
+        np.random.default_rng(seed + 911).random(pop.n) < share)
+    return np.where(miner, np.char.add('mining_', d_names), '')
+
+
+def school_census_columns(pop: Population, n_districts, status_names=None):
+    """Census columns of the school-phase scenarios (scenario_models.py:356-440): pupils get a school of ~400 in
+    their home district (`school_id`, `school_id_district`) and a re-opening phase 1..5 by age band (`phase`)."""
+    status_names = list(C.ECONOMIC_STATUS_NAMES if status_names is None else status_names)
+    d_names = np.array(district_names(n_districts))[pop.district]
+    pupil = pop.status == status_names.index('In School')
+    school_no = (np.cumsum(pupil) // 400).astype(str)
+    return dict(school_id=np.where(pupil, np.char.add(np.char.add('s_', d_names), np.char.add('_', school_no)), ''),
+                school_id_district=np.where(pupil, d_names, ''), phase=np.where(pupil, 1 + (pop.age % 5), 0))
+
+
 def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=None, school_columns=False,
                             mining_columns=False, mining_share=0.04):
     """Census-style DataFrame with the columns `Country.load_agents` reads.
@@ -183,18 +204,10 @@ def population_to_dataframe(pop: Population, n_districts, seed=0, status_names=N
     for k, v in pop.extras.items():
         df[k] = v
     if school_columns:
-        # pupils get a school of ~400 in their home district and a re-opening phase 1..5 by age band
-        pupil = pop.status == list(status_names).index('In School')
-        school_no = (np.cumsum(pupil) // 400).astype(str)
-        df['school_id'] = np.where(pupil, np.char.add(np.char.add('s_', d_names), np.char.add('_', school_no)), '')
-        df['school_id_district'] = np.where(pupil, d_names, '')
-        df['phase'] = np.where(pupil, 1 + (pop.age % 5), 0)
+        for column, values in school_census_columns(pop, n_districts, status_names).items():
+            df[column] = values
     if mining_columns:
-        # a share of the adult workers of every fifth district live and work in that district's mining camp (census
-        # column `mining_district_id` = 'mining_<district>', scenario_models.py:232-236; census notebook cells 41, 44)
-        miner = (pop.district % 5 == 2) & (pop.status >= 3) & (pop.status <= 6) & (pop.age >= 18) & (
-            np.random.default_rng(seed + 911).random(pop.n) < mining_share)
-        df['mining_district_id'] = np.where(miner, np.char.add('mining_', d_names), '')
+        df['mining_district_id'] = mining_camp_column(pop, n_districts, seed, mining_share)
     return df
 
 

@@ -27,6 +27,10 @@ def build_world(root, ref):
         names = np.array(synth.district_names(ref['n_districts']))
         pop.extras['manufacturing_workers'] = np.where(pop.extras['manufacturing_workers'] == 1, 1.0, np.nan)
         pop.extras['school_id_district'] = np.where(pop.extras['school_goers'] == 1, names[pop.district], '')
+    if ref['case'] == 'open_mining_100k':
+        pop.extras['mining_district_id'] = synth.mining_camp_column(pop, ref['n_districts'], POP_SEED, 0.15)
+    if ref['case'] == 'accelerated_schools_100k':
+        pop.extras.update(synth.school_census_columns(pop, ref['n_districts']))
     cases = synth.seed_case_counts(pop, spec, seed=POP_SEED)
     synth.write_data_dir(root, spec, pop, seed_cases=cases, seed=0)
     os.environ['COVID19_ABM_DATA_DIR'] = root

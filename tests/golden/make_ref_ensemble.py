@@ -30,7 +30,14 @@ CASES = {
     'selective_lockdown_100k': ('LockdownGreatestMobilityScenario', 100_000, 60, 45, 200, 32, 1.9),
     # BASELINE.json configs[3]: continued lockdown with schools and manufacturing re-opened
     'open_manufacturing_schools_100k': ('OpenManufacturingAndSchoolsScenario', 100_000, 60, 45, 200, 32, 1.9),
+    # BASELINE.json configs[3]: continued lockdown with the mines open (camps = households of tens to hundreds of miners)
+    'open_mining_100k': ('OpenMiningScenario', 100_000, 60, 45, 200, 32, 1.9),
+    # school-phase scenario -- schools are extra infection pools, one more phase opens on 1 October
+    'accelerated_schools_100k': ('AcceleratedGovernmentOpenSchoolsScenario', 100_000, 60, 45, 200, 32, 1.9),
+    'isolate_symptomatic_100k': ('IsolateSymptomaticScenario', 100_000, 60, 45, 200, 32, 1.9),
+    'handwashing_risk_100k': ('HandWashingRiskScenario', 100_000, 60, 45, 200, 32, 1.9),
 }
+MINING_SHARE = 0.15
 POP_SEED = 2020
 
 
@@ -54,6 +61,10 @@ def member(args):
     pop = synth.make_population(n_agents, spec, seed=POP_SEED, scenario_flags=True)
     if case in ('selective_lockdown_100k', 'open_manufacturing_schools_100k'):
         pop = scenario_columns(pop, D)
+    if case == 'open_mining_100k':
+        pop.extras['mining_district_id'] = synth.mining_camp_column(pop, D, POP_SEED, MINING_SHARE)
+    if case == 'accelerated_schools_100k':
+        pop.extras.update(synth.school_census_columns(pop, D))
     cases = synth.seed_case_counts(pop, spec, seed=POP_SEED)
     world = rh.RefWorld(spec, pop, seed_cases=cases)
     log_file = os.path.join(world.tmp, 'logs', 'model.log')
