@@ -139,27 +139,41 @@ def compare(ref_state, oracle, where):
 
 
 def run_case(name, scenario, n_agents, n_districts, n_steps, seed, philox_seed, snapshot_every, infect_num,
-             start=datetime(2020, 9, 1, 0)):
+             start=datetime(2020, 9, 1, 0), school_columns=False, open_phases=None):
     spec0 = synth.make_spec(n_districts=n_districts, R0=2.6, seed=seed, start_datetime=start)
     pop = synth.make_population(n_agents, spec0, seed=seed, scenario_flags=True)
+    if school_columns:                 # census columns of the school-phase scenarios (school_id, phase, ...)
+        pop.extras.update(synth.school_census_columns(pop, n_districts))
     seeds = synth.pick_seeds(pop, spec0, infect_num=infect_num, seed=seed)
     world = rh.RefWorld(spec0, pop, seed_cases={0: 1})
     log_file = os.path.join(world.tmp, 'logs', 'model.log')
     try:
         model = world.make_model(scenario, seed_infected=1, log_file=log_file, infect=False)
         params = model.params
-        spec = rh.spec_from_reference_params(params, spec0.step_minutes, start)
+        if open_phases:                # what Country.step's clock hook does on the 1st of a month (base_model.py:812-819)
+            model.active_school_phases = list(open_phases)
+            model.open_schools(np.unique(model.district_ids), model.active_school_phases)
+        n_schools = len(params.SCHOOL_ID_TO_NAME) if getattr(model, 'is_school_scenario', False) else 0
+        spec = rh.spec_from_reference_params(params, spec0.step_minutes, start, n_extra_pools=n_schools)
         # population as the reference holds it after its own (scenario) initialisation
         pop.district_mover = np.asarray(model.district_mover).astype(np.int8)
         pop.move_prob_weekday = np.asarray(model.economic_status_weekday_movement_probability, dtype=np.float64).copy()
         pop.move_prob_other = np.asarray(model.economic_status_other_day_movement_probability, dtype=np.float64).copy()
         assert np.array_equal(np.asarray(model.district_ids), pop.district)
-        # where the scenario hook sends people at 08:00 (IsolateVulnerable keeps the elderly in their household)
+        assert np.array_equal(np.asarray(model.household_ids), pop.household + n_districts)
+        # where the scenario hook sends people at 08:00 (IsolateVulnerable keeps the elderly in their household; the
+        # school-phase scenarios send the pupils of the open phases to their school, an outside location numbered
+        # after the households, base_model.py:583-591, 801-805)
         econ = np.asarray(model.economic_activity_location_ids).astype(np.int64)
         at_household = econ == np.asarray(model.household_ids)
-        assert (at_household | (econ == np.asarray(model.district_ids))).all()
-        pop.econ_kind = np.where(at_household, rh.C.EKIND_HOUSEHOLD, rh.C.EKIND_HOME_DISTRICT).astype(pop.econ_kind.dtype)
-        assert np.array_equal(np.asarray(model.household_ids), pop.household + n_districts)
+        first_school = n_districts + pop.n_households
+        at_school = econ >= first_school if n_schools else np.zeros(pop.n, dtype=bool)
+        assert (at_household | at_school | (econ == np.asarray(model.district_ids))).all()
+        pop.econ_kind = np.where(at_household, rh.C.EKIND_HOUSEHOLD,
+                                 np.where(at_school, rh.C.EKIND_POOL, rh.C.EKIND_HOME_DISTRICT)).astype(pop.econ_kind.dtype)
+        if n_schools:
+            assert min(params.SCHOOL_ID_TO_NAME) == first_school and at_school.sum() > 50
+            pop.econ_pool = np.where(at_school, n_districts + (econ - first_school), 0).astype(np.int32)
         tab = tables.build_tables(spec)
         par = dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob)
         oracle = OracleModel(pop, par, tab, philox_seed)
@@ -233,6 +247,9 @@ def run_case(name, scenario, n_agents, n_districts, n_steps, seed, philox_seed, 
             spec_hw_risk=np.zeros(0) if spec.hw_risk is None else spec.hw_risk,
             ref_log=json.dumps(ref_log),
         )
+        if n_schools:
+            out['spec_n_extra_pools'] = n_schools
+            out['pop_econ_pool'] = pop.econ_pool
         for i, st in enumerate(snaps):
             for key, val in st.items():
                 small = val.astype(np.int32) if val.dtype == np.int64 else val
@@ -255,3 +272,5 @@ if __name__ == '__main__':
              seed=15, philox_seed=0x5EED0005, snapshot_every=60, infect_num=50)
     run_case('block_mobility', 'BlockGreatestMobilityScenario', n_agents=2500, n_districts=12, n_steps=6 * 30,
              seed=16, philox_seed=0x5EED0006, snapshot_every=60, infect_num=50)
+    run_case('open_school_phases', 'AcceleratedGovernmentOpenSchoolsScenario', n_agents=4000, n_districts=5, n_steps=6 * 30,
+             seed=17, philox_seed=0x5EED0007, snapshot_every=60, infect_num=60, school_columns=True, open_phases=[1, 2, 3])

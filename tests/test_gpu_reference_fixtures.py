@@ -1,9 +1,10 @@
 """Second batch of reference pins on the GPU (this file runs after test_gpu_parity.py).
 
-1. CUDA path vs the real reference's functions on three more scenarios (fixtures added after
+1. CUDA path vs the real reference's functions on four more scenarios (fixtures added after
 test_gpu_parity.py::test_cuda_matches_reference_fixture's first three): the hand-washing risk multiplier per district
-(`HandWashingRiskScenario`), the elderly kept in their households (`IsolateVulnerableScenario`) and travel blocked out
-of the most mobile districts (`BlockGreatestMobilityScenario`).  Same bar: every state, location and tick vector and
+(`HandWashingRiskScenario`), the elderly kept in their households (`IsolateVulnerableScenario`), travel blocked out
+of the most mobile districts (`BlockGreatestMobilityScenario`) and pupils of three open phases attending their schools
+-- outside locations numbered after the households (`AcceleratedGovernmentOpenSchoolsScenario` after `open_schools`).  Same bar: every state, location and tick vector and
 every log counter bit-exact at every stored snapshot.
 2. Tier-2 ensembles (tolerance and method: test_gpu_ensemble.py) for four more scenarios of the real reference: the mines
 open under lockdown (camp households of tens to hundreds), a school-phase scenario (schools as extra infection pools, one
@@ -20,7 +21,7 @@ from util import assert_state_equal, load_fixture
 
 pytestmark = pytest.mark.gpu
 
-CASES = ['handwashing_risk', 'isolate_vulnerable', 'block_mobility']
+CASES = ['handwashing_risk', 'isolate_vulnerable', 'block_mobility', 'open_school_phases']
 
 
 def replay(name, simulation_class):

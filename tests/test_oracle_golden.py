@@ -6,7 +6,8 @@ from oracle.abm_oracle import OracleModel
 from abm_b200 import tables
 from util import assert_state_equal, load_fixture, oracle_params
 
-CASES = ['unmitigated', 'isolate_symptomatic', 'lockdown', 'handwashing_risk', 'isolate_vulnerable', 'block_mobility']
+CASES = ['unmitigated', 'isolate_symptomatic', 'lockdown', 'handwashing_risk', 'isolate_vulnerable', 'block_mobility',
+         'open_school_phases']
 
 
 @pytest.mark.parametrize('name', CASES)

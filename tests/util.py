@@ -25,10 +25,12 @@ def load_fixture(name):
                      start_datetime=start, interaction_matrix=z['spec_interaction_matrix'],
                      interaction_sizes=z['spec_interaction_sizes'], od_cum=z['spec_od_cum'],
                      stay_mean=z['spec_stay_mean'], stay_std=z['spec_stay_std'],
-                     hw_risk=hw if hw.size else None, mild_symptom_move_prob=float(z['spec_mild']))
+                     hw_risk=hw if hw.size else None, mild_symptom_move_prob=float(z['spec_mild']),
+                     n_extra_pools=int(z['spec_n_extra_pools']) if 'spec_n_extra_pools' in z.files else 0)
     pop = Population(district=z['pop_district'], household=z['pop_household'], age=z['pop_age'], status=z['pop_status'],
                      econ_kind=z['pop_econ_kind'], district_mover=z['pop_district_mover'],
-                     move_prob_weekday=z['pop_move_prob_weekday'], move_prob_other=z['pop_move_prob_other'])
+                     move_prob_weekday=z['pop_move_prob_weekday'], move_prob_other=z['pop_move_prob_other'],
+                     econ_pool=z['pop_econ_pool'] if 'pop_econ_pool' in z.files else None)      # schools as pools
     snaps = []
     for i, k in enumerate(z['snap_steps']):
         snaps.append((int(k), {key: z[f'snap{i}_{key}'] for key in STATE_KEYS}))
