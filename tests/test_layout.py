@@ -67,3 +67,56 @@ def test_pack_unpack_roundtrip_initial_state():
     assert np.all(st['date_died'] == C.T_NEVER) and np.all(st['infected_at_location_ids'] == -1)
     fill = flags[sm.agent_of < 0]
     assert np.all(fill & C.F_FILLER) and np.all((fill & 7) == C.STATE_DEAD)
+
+
+def test_slot_map_properties_on_random_households():
+    """Property test: any grouping into households (sizes 1..90, i.e. below and above the 32-member tile), any
+    district boundaries and any id base give a slot map that keeps the canonical order, never splits a small household
+    or a lane's four-id group across sub-tiles, keeps one home district per sub-tile and numbers slots by id."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(sizes=st.lists(st.integers(1, 90), min_size=1, max_size=120),
+           n_districts=st.integers(1, 5), base=st.integers(0, 2 ** 40), seed=st.integers(0, 2 ** 31))
+    def check(sizes, n_districts, base, seed):
+        rng = np.random.default_rng(seed)
+        hh = np.repeat(np.arange(len(sizes), dtype=np.int64), sizes)
+        hh_district = np.sort(rng.integers(0, n_districts, len(sizes)))          # households grouped by district
+        district = hh_district[hh].astype(np.int32)
+        sm = layout.build_slot_map(hh, district, agent_id_base=base)
+        S = C.SUBTILE
+        n = hh.shape[0]
+        assert sm.n_slots % C.TILE == 0 and sm.n_subtiles * S == sm.n_slots
+        assert np.all(np.diff(sm.slot_of) > 0) and sm.slot_of[-1] < sm.n_slots
+        sub = sm.slot_of // S
+        size_of = np.asarray(sizes)[hh]
+        head_sub = sub[np.r_[0, np.cumsum(sizes)[:-1]]][hh]
+        assert np.all(sub[size_of <= C.BIG_HOUSEHOLD] == head_sub[size_of <= C.BIG_HOUSEHOLD])
+        sub_base = (sm.sub_info & np.uint64((1 << 48) - 1)).astype(np.int64)
+        home = (sm.sub_info >> np.uint64(48)).astype(np.int64)
+        assert np.all(sub_base % 4 == 0)
+        assert np.array_equal(sub_base[sub] + sm.slot_of % S, np.arange(n) + base)
+        assert np.array_equal(home[sub], district)
+        big = [i for i, s in enumerate(sizes) if s > C.BIG_HOUSEHOLD]
+        assert sm.big_size.tolist() == [sizes[i] for i in big]
+        starts = np.r_[0, np.cumsum(sizes)[:-1]]
+        assert sm.big_start[:-1].tolist() == [int(starts[i]) + base for i in big]
+        a = sm.agent_of
+        assert np.array_equal(a[sm.slot_of], np.arange(n)) and (a >= 0).sum() == n
+        # the household index inside the sub-tile that the kernel's segmented sum uses
+        pop = synth.Population(district=district, household=hh, age=np.zeros(n, np.int32), status=np.zeros(n, np.int32),
+                               econ_kind=np.zeros(n, np.int8), district_mover=np.zeros(n, np.int8),
+                               move_prob_weekday=np.ones(n), move_prob_other=np.ones(n))
+        flags, aux = layout.pack_flags(pop, sm)
+        idx = layout.household_index(flags).view(np.uint8)
+        real = a >= 0
+        per_slot_hh = np.where(real, hh[np.maximum(a, 0)], -1)
+        for u in np.unique(sub):
+            sl = slice(u * S, (u + 1) * S)
+            small = real[sl] & (np.asarray(sizes)[np.maximum(per_slot_hh[sl], 0)] <= C.BIG_HOUSEHOLD)
+            if small.any():
+                hh_here, ix_here = per_slot_hh[sl][small], idx[sl][small]
+                # same household <-> same index, and indices are dense from 0 in slot order
+                assert len(set(zip(hh_here.tolist(), ix_here.tolist()))) == len(set(hh_here.tolist())) == len(set(ix_here.tolist()))
+
+    check()
