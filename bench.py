@@ -157,8 +157,11 @@ def run_reference_arm(a):
     line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=days, warmup=warm,
                 ms_per_step=wall / days * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='int64',
                 data='synthetic',
-                config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.districts} districts, unmitigated R0=1.9, '
-                                     '4 h sub-steps', agents_per_replica=n, replicas=procs),
+                config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.agents_per_gpu} agents per GPU x {a.gpus} GPU(s), '
+                                     f'{a.districts} districts, unmitigated R0=1.9, 4 h sub-steps (6 per simulated day)',
+                            sample=f'CPU arm: bounded sample of that workload -- {procs} independent replicas of {n} agents '
+                                   f'each (same generator, same districts), {days} day(s) after {warm} warm-up day(s)',
+                            agents_per_replica=n, replicas=procs),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind='port', sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
