@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument('--cpu-agents', type=int, default=1_500_000, help='agents of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--shards', default='contiguous', choices=['contiguous', 'dealt'],
+                    help='multi-GPU sharding: contiguous ranges of the canonical order, or one piece of every district per rank')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: sum the tables over ranks inside the table kernel through peer memory, or with ncclAllReduce')
     ap.add_argument('--full-run-days', type=int, default=365, help='also time a whole run of this many days from the seeding (0 = skip)')
@@ -185,11 +187,17 @@ def run_cuda_arm(a):
     n_total = a.agents_per_gpu * world
     spec = synth.make_spec(n_districts=a.districts, R0=1.9, seed=POP_SEED)
     tab = tables.build_tables(spec)
-    pop, base, dstart = sharding.make_synthetic_shard(n_total, spec, POP_SEED, world, rank)
-    local_seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=POP_SEED + rank) + base
-
     from abm_b200.engine import HostStore
-    store = HostStore(spec, pop, agent_id_base=base)         # ingestion (slot map, bit packing, page-locking): untimed
+    agent_ids = None
+    if a.shards == 'dealt' and world > 1:
+        pop, agent_ids, dstart = sharding.make_synthetic_shard_dealt(n_total, spec, POP_SEED, world, rank)
+        base = int(agent_ids[0])
+        local_seeds = agent_ids[synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=POP_SEED + rank)]
+        store = HostStore(spec, pop, agent_ids=agent_ids)
+    else:
+        pop, base, dstart = sharding.make_synthetic_shard(n_total, spec, POP_SEED, world, rank)
+        local_seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=POP_SEED + rank) + base
+        store = HostStore(spec, pop, agent_id_base=base)     # ingestion (slot map, bit packing, page-locking): untimed
     max_days = max(a.spinup + a.warmup + 2 * a.steps + 16, a.full_run_days + 8)
 
     def make_sim(upload=True):
@@ -198,7 +206,7 @@ def run_cuda_arm(a):
             uid = distributed.exchange_unique_id(lib, rank, world, device)       # one id per communicator
         return Simulation(spec, pop, seed=POP_SEED, device=local, tables=tab, max_days=max_days, agent_id_base=base,
                           district_start=dstart, world_size=world, rank=rank, nccl_unique_id=uid, host_store=store,
-                          upload=upload, exchange=a.exchange if world > 1 else None)
+                          upload=upload, exchange=a.exchange if world > 1 else None, agent_ids=agent_ids)
 
     def barrier():
         if world > 1:
@@ -334,7 +342,8 @@ def run_cuda_arm(a):
             higher_is_better=True, scaling='weak', vs_baseline=None, dtype='u32/int64', data='synthetic',
             config=dict(workload=f'synthetic Zimbabwe-shaped population, {a.agents_per_gpu} agents per GPU x {world} GPU(s), '
                                  f'{a.districts} districts, unmitigated R0=1.9, 4 h sub-steps (6 per simulated day), '
-                                 f'household-aligned shards' + ('' if world == 1 else (
+                                 f'household-aligned shards' + (' (one piece of every district per rank)' if agent_ids is not None else '')
+                                 + ('' if world == 1 else (
                                      ', district x status tables summed over ranks inside the table kernel through peer '
                                      'memory (NVLink)' if a.exchange == 'p2p' else ', ncclAllReduce of the district x status '
                                      'tables per sub-step')),

@@ -114,10 +114,11 @@ class HostStore:
     per-agent vectors in device layout.  Building it (slot map, bit packing) is ingestion work; uploading
     it is a plain host -> device copy of `nbytes` bytes."""
 
-    def __init__(self, spec: ModelSpec, pop: Population, agent_id_base=0):
+    def __init__(self, spec: ModelSpec, pop: Population, agent_id_base=0, agent_ids=None):
         import torch
-        self.spec, self.pop, self.agent_id_base = spec, pop, int(agent_id_base)
-        self.sm = layout.build_slot_map(pop.household, pop.district, agent_id_base)
+        self.spec, self.pop, self.agent_id_base = spec, pop, int(agent_id_base if agent_ids is None else agent_ids[0])
+        self.agent_ids = None if agent_ids is None else np.ascontiguousarray(agent_ids, dtype=np.int64)
+        self.sm = layout.build_slot_map(pop.household, pop.district, agent_id_base, agent_ids=self.agent_ids)
         sm = self.sm
         self.move_class, self.move_thr, _ = tables_mod.move_classes(pop, spec.mild_symptom_move_prob)
         flags, aux = layout.pack_flags(pop, sm)
@@ -155,12 +156,14 @@ class Simulation:
 
     pop            canonical-order agents of this rank (household-aligned shard)
     agent_id_base  canonical id of pop's first agent (Philox key; makes results independent of sharding)
+    agent_ids      canonical id of every agent of pop, for shards that are not one contiguous range of the canonical
+                   order (sharding.deal_population); overrides agent_id_base
     district_start global canonical id of the first agent of every home district [D + 1]
     """
 
     def __init__(self, spec: ModelSpec, pop: Population, seed=0, device=0, tables=None, max_days=400,
                  agent_id_base=0, district_start=None, world_size=1, rank=0, nccl_unique_id=None, use_graph=True,
-                 host_store=None, upload=True, use_pdl=True, exchange=None):
+                 host_store=None, upload=True, use_pdl=True, exchange=None, agent_ids=None):
         """exchange (world_size > 1): 'p2p' sums the district x status tables over ranks inside the table kernel through
         peer memory (one node; needs an initialised torch.distributed group to trade the buffer handles), 'nccl' uses
         ncclAllReduce (needs `nccl_unique_id`).  Default: 'p2p' unless a unique id is given."""
@@ -175,9 +178,14 @@ class Simulation:
         torch.cuda.set_device(self.device)
         # all device work of this simulation (uploads, kernels, graph replays) is ordered on one stream
         self.stream = torch.cuda.Stream(device=self.device)
-        hs = host_store if host_store is not None else HostStore(spec, pop, agent_id_base)
+        hs = host_store if host_store is not None else HostStore(spec, pop, agent_id_base, agent_ids=agent_ids)
+        if agent_ids is None and hs.agent_ids is not None:
+            agent_ids = hs.agent_ids
+        if agent_ids is not None:
+            agent_id_base = int(agent_ids[0])
         if hs.pop is not pop or hs.agent_id_base != int(agent_id_base):
             raise ValueError('host_store was built for another population / id base')
+        self.agent_ids = hs.agent_ids
         self.host_store = hs
         self.sm = hs.sm
         sm = self.sm
@@ -269,7 +277,12 @@ class Simulation:
     def seed_infections(self, agent_ids):
         """Country.set_epidemic_status(ids) at the current time (base_model.py:796)."""
         ids = np.ascontiguousarray(agent_ids, dtype=np.int64)
-        local = ids - self.sm.agent_id_base
+        if self.agent_ids is None:
+            local = ids - self.sm.agent_id_base
+        else:                                  # shard made of several id runs: look the ids up
+            local = np.searchsorted(self.agent_ids, ids)
+            if ids.size and (local.max() >= self.agent_ids.shape[0] or not np.array_equal(self.agent_ids[local], ids)):
+                raise ValueError('seed ids outside this rank\'s shard')
         slots = np.ascontiguousarray(self.sm.slot_of[local])
         self._check(self.lib.abm_seed(self.h, _ptr(slots), _ptr(ids), ids.shape[0]))
 

@@ -48,6 +48,7 @@ class SlotMap:
     big_start: np.ndarray      # int64 [n_big + 1] global id of first member of each big household (+ sentinel)
     big_size: np.ndarray       # int64 [n_big]
     agent_id_base: int
+    sub_id: np.ndarray = None  # int64 [n_subtiles] global id of the first agent of each sub-tile (None: contiguous ids)
     _agent_of: np.ndarray = None
 
     @property
@@ -66,15 +67,27 @@ class SlotMap:
     @property
     def sub_info(self):
         """uint64 [n_subtiles]: canonical id of slot 0 (a multiple of 4) | home district << 48."""
-        base = self.sub_first[:-1] + self.agent_id_base - self.sub_lead
+        first_id = self.sub_first[:-1] + self.agent_id_base if self.sub_id is None else self.sub_id
+        base = first_id - self.sub_lead
         return (base.astype(np.uint64) | (self.sub_home.astype(np.uint64) << np.uint64(48)))
 
 
-def build_slot_map(household: np.ndarray, district: np.ndarray, agent_id_base: int = 0) -> SlotMap:
-    """Greedy sub-tile packing.  Units are whole small households and single members of big ones."""
+def build_slot_map(household: np.ndarray, district: np.ndarray, agent_id_base: int = 0, agent_ids=None) -> SlotMap:
+    """Greedy sub-tile packing.  Units are whole small households and single members of big ones.
+
+    `agent_ids` (optional, int64 [n], strictly increasing): the global canonical id of every agent when the shard is
+    not one contiguous range of the canonical order (e.g. one piece of every district); ids then run contiguously
+    inside a run and a new run starts a new sub-tile, so that slot offset o of a sub-tile still holds id base + o."""
     n = int(household.shape[0])
     if n == 0:
         raise ValueError('empty population')
+    if agent_ids is None:
+        ids = None
+    else:
+        ids = np.ascontiguousarray(agent_ids, dtype=np.int64)
+        if ids.shape[0] != n or (n > 1 and np.any(np.diff(ids) <= 0)):
+            raise ValueError('agent_ids must be strictly increasing, one per agent')
+        agent_id_base = int(ids[0])
     head = np.empty(n, dtype=bool)
     head[0] = True
     head[1:] = household[1:] != household[:-1]
@@ -90,10 +103,13 @@ def build_slot_map(household: np.ndarray, district: np.ndarray, agent_id_base: i
     m = unit_start.shape[0]
     # a sub-tile never continues into another home district
     d_unit = np.asarray(district)[unit_start]
-    brk = np.nonzero(np.r_[True, d_unit[1:] != d_unit[:-1]])[0]         # units that start a district
+    new_run = d_unit[1:] != d_unit[:-1]                                  # units that start a district ...
+    if ids is not None:                                                  # ... or a new run of consecutive ids
+        new_run = new_run | (ids[unit_start[1:]] != ids[unit_start[1:] - 1] + 1)
+    brk = np.nonzero(np.r_[True, new_run])[0]
     next_brk = np.r_[brk[1:], m][np.searchsorted(brk, np.arange(m), side='right') - 1]
     # capacity of a sub-tile that starts with unit i: the leading (id & 3) slots are fillers
-    lead_unit = (unit_start + agent_id_base) & 3
+    lead_unit = ((unit_start + agent_id_base) if ids is None else ids[unit_start]) & 3
     nxt = np.minimum(np.searchsorted(unit_end, unit_start + (C.SUBTILE - lead_unit), side='right'), next_brk)
     if np.any(nxt <= np.arange(m)):
         raise RuntimeError('placement unit larger than a sub-tile')
@@ -117,15 +133,20 @@ def build_slot_map(household: np.ndarray, district: np.ndarray, agent_id_base: i
     shift = np.arange(n_sub_used, dtype=np.int64) * C.SUBTILE + sub_lead - sub_first[:-1]
     slot_of = np.arange(n, dtype=np.int64) + np.repeat(shift, counts)
     # empty trailing sub-tiles: all fillers, ids past the last agent (rounded up to a multiple of 4)
-    end_id = n + agent_id_base
+    end_id = n + agent_id_base if ids is None else int(ids[-1]) + 1
     pad_lead = np.full(pad, end_id & 3, dtype=np.int64)       # keeps base = end_id - lead a multiple of 4
     sub_first = np.r_[sub_first, np.full(pad, n, dtype=np.int64)]
     sub_lead = np.r_[sub_lead, pad_lead]
     sub_home = np.r_[sub_home, np.zeros(pad, dtype=np.int64)]
-    big_start = np.append(starts[big], n).astype(np.int64) + agent_id_base
+    if ids is None:
+        big_start = np.append(starts[big], n).astype(np.int64) + agent_id_base
+        sub_id = None
+    else:
+        big_start = np.append(ids[starts[big]], end_id).astype(np.int64)
+        sub_id = np.r_[ids[sub_first[:n_sub_used]], np.full(pad, end_id, dtype=np.int64)]
     return SlotMap(n_agents=n, n_tiles=n_tiles, n_subtiles=n_tiles * SUBS_PER_TILE, sub_first=sub_first,
                    sub_lead=sub_lead, sub_home=sub_home, slot_of=slot_of, big_start=big_start,
-                   big_size=sizes[big].astype(np.int64), agent_id_base=int(agent_id_base))
+                   big_size=sizes[big].astype(np.int64), agent_id_base=int(agent_id_base), sub_id=sub_id)
 
 
 def pack_flags(pop: Population, sm: SlotMap):

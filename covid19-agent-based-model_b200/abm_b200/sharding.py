@@ -6,6 +6,14 @@ local.  District pools are global: each rank accumulates partial district x stat
 agents (travellers contribute to their destination row from their home rank -- no agent ever migrates)
 and one all-reduce per sub-step sums them.  Random draws are keyed by the
 global canonical agent id, so trajectories do not depend on the number of ranks.
+
+Two ways to cut (both household-aligned, both give bit-identical trajectories):
+  contiguous  rank r holds the r-th of `world_size` ranges of the canonical order (`split_population`,
+              `make_synthetic_shard`): a few whole districts per rank;
+  dealt       rank r holds the r-th piece of EVERY district (`deal_population`, `make_synthetic_shard_dealt`): every
+              rank sees the same mix of districts, hence the same epidemic phase and the same amount of rare-event
+              work per sub-step -- less waiting in the per-sub-step table exchange.  The shard is then a sequence of
+              id runs; the slot map takes the per-agent global ids (layout.build_slot_map(agent_ids=...)).
 """
 import numpy as np
 
@@ -68,3 +76,62 @@ def make_synthetic_shard(n_agents, spec: ModelSpec, seed, world_size, rank):
     lo = snap_to_household(part.household, lo_nom - base)
     hi = part.n if rank == world_size - 1 and d_hi == spec.n_districts else snap_to_household(part.household, min(hi_nom - base, part.n))
     return slice_population(part, lo, hi), base + lo, dstart
+
+
+def deal_population(pop: Population, world_size):
+    """Per rank, the indices (into the canonical order) of its dealt shard: piece r of every home district, pieces
+    cut at household boundaries near the r/world_size quantiles of the district."""
+    D = int(pop.district.max()) + 1 if pop.n else 0
+    dstart = np.searchsorted(pop.district, np.arange(D + 1)).astype(np.int64)
+    parts = [[] for _ in range(world_size)]
+    for d in range(D):
+        lo, hi = int(dstart[d]), int(dstart[d + 1])
+        if hi == lo:
+            continue
+        hh = pop.household[lo:hi]
+        cuts = [snap_to_household(hh, ((hi - lo) * r) // world_size) for r in range(world_size)] + [hi - lo]
+        for r in range(world_size):
+            if cuts[r + 1] > cuts[r]:
+                parts[r].append(np.arange(lo + cuts[r], lo + cuts[r + 1], dtype=np.int64))
+    return [np.concatenate(p) if p else np.zeros(0, dtype=np.int64) for p in parts]
+
+
+def take_population(pop: Population, idx):
+    """The agents `idx` (increasing, whole households) as a Population with dense local household numbers."""
+    hh = pop.household[idx]
+    dense = np.cumsum(np.r_[0, hh[1:] != hh[:-1]]) if idx.shape[0] else hh
+    return Population(district=pop.district[idx], household=dense.astype(np.int64), age=pop.age[idx], status=pop.status[idx],
+                      econ_kind=pop.econ_kind[idx], district_mover=pop.district_mover[idx],
+                      move_prob_weekday=pop.move_prob_weekday[idx], move_prob_other=pop.move_prob_other[idx],
+                      econ_pool=None if pop.econ_pool is None else pop.econ_pool[idx],
+                      extras={k: v[idx] for k, v in pop.extras.items()})
+
+
+def make_synthetic_shard_dealt(n_agents, spec: ModelSpec, seed, world_size, rank):
+    """This rank's dealt shard of the synthetic population: (pop_shard, agent_ids, district_start_global).
+
+    Every district is generated from its own RNG stream (the same agents `make_population` builds in one piece), cut
+    into `world_size` household-aligned pieces, and piece `rank` is kept -- one district in memory at a time."""
+    counts = district_counts(n_agents, spec, seed)
+    dstart = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    pieces, ids, hh_next = [], [], 0
+    for d in range(spec.n_districts):
+        if counts[d] == 0:
+            continue
+        part = synth.make_population(n_agents, spec, seed=seed, district_range=(d, d + 1))
+        n = part.n
+        cuts = [snap_to_household(part.household, (n * r) // world_size) for r in range(world_size)] + [n]
+        lo, hi = cuts[rank], cuts[rank + 1]
+        if hi <= lo:
+            continue
+        piece = slice_population(part, lo, hi)
+        piece.household = piece.household + hh_next
+        hh_next = int(piece.household[-1]) + 1
+        pieces.append(piece)
+        ids.append(np.arange(lo, hi, dtype=np.int64) + int(dstart[d]))
+    cat = lambda name: np.concatenate([getattr(p, name) for p in pieces])
+    pop = Population(district=cat('district'), household=cat('household'), age=cat('age'), status=cat('status'),
+                     econ_kind=cat('econ_kind'), district_mover=cat('district_mover'),
+                     move_prob_weekday=cat('move_prob_weekday'), move_prob_other=cat('move_prob_other'),
+                     extras={k: np.concatenate([p.extras[k] for p in pieces]) for k in pieces[0].extras})
+    return pop, np.concatenate(ids), dstart

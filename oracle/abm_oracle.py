@@ -98,16 +98,19 @@ class OracleModel:
     par : dict with od_cum [7,D,D], mild_prob, and optional hw flag
     tab : dict of host-built tables (see covid19-agent-based-model_b200/abm_b200/tables.py)
     agent_id_base : global id of local agent 0 (Philox key) for household-aligned shards
+    agent_ids : global id of every local agent, for shards that are not one contiguous range (overrides the base)
     reduce_fn : callable(np.ndarray uint64) -> summed over ranks (None = single rank)
     """
 
-    def __init__(self, pop, par, tab, seed, agent_id_base=0, reduce_fn=None):
+    def __init__(self, pop, par, tab, seed, agent_id_base=0, reduce_fn=None, agent_ids=None):
         self.tab, self.par, self.seed = tab, par, int(seed)
         self.reduce_fn = reduce_fn
         n = pop.district.shape[0]
         self.n = n
         self.D, self.A, self.P = tab['n_districts'], tab['n_status'], tab['n_pools']
-        self.agent_ids = np.arange(n, dtype=np.int64) + int(agent_id_base)
+        # global canonical ids (the Philox keys): one contiguous range, or given per agent for a shard made of several
+        self.agent_ids = (np.arange(n, dtype=np.int64) + int(agent_id_base) if agent_ids is None
+                          else np.ascontiguousarray(agent_ids, dtype=np.int64))
         self.step_ticks = tab['step_ticks']
         self.k = 0
         # --- agent vectors (base_model.py:572-634)

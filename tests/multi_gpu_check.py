@@ -27,6 +27,8 @@ def main():
     ap.add_argument('--districts', type=int, default=8)
     ap.add_argument('--days', type=int, default=20)
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'])
+    ap.add_argument('--shards', default='contiguous', choices=['contiguous', 'dealt'],
+                    help='contiguous ranges of the canonical order, or one piece of every district per rank')
     a = ap.parse_args()
 
     import torch
@@ -43,14 +45,23 @@ def main():
     pop = synth.make_population(a.agents, spec, seed=41)
     seeds = synth.pick_seeds(pop, spec, infect_num=max(50, a.agents // 400), seed=41)
     tab = tables.build_tables(spec)
-    lo, hi = sharding.split_population(pop, world)[rank]
-    shard = sharding.slice_population(pop, lo, hi)
     dstart = np.searchsorted(pop.district, np.arange(spec.n_districts + 1)).astype(np.int64)
     uid = distributed.exchange_unique_id(lib, rank, world, device) if (world > 1 and a.exchange == 'nccl') else None
-    sim = Simulation(spec, shard, seed=4242, device=local, tables=tab, agent_id_base=lo, district_start=dstart,
-                     world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4,
-                     exchange=a.exchange if world > 1 else None)
-    sim.seed_infections(seeds[(seeds >= lo) & (seeds < hi)])
+    if a.shards == 'dealt':
+        idx = sharding.deal_population(pop, world)[rank]               # global ids of this rank's agents
+        shard = sharding.take_population(pop, idx)
+        lo, hi = int(idx[0]), int(idx[-1]) + 1
+        sim = Simulation(spec, shard, seed=4242, device=local, tables=tab, agent_ids=idx, district_start=dstart,
+                         world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4,
+                         exchange=a.exchange if world > 1 else None)
+    else:
+        lo, hi = sharding.split_population(pop, world)[rank]
+        shard = sharding.slice_population(pop, lo, hi)
+        idx = np.arange(lo, hi, dtype=np.int64)
+        sim = Simulation(spec, shard, seed=4242, device=local, tables=tab, agent_id_base=lo, district_start=dstart,
+                         world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4,
+                         exchange=a.exchange if world > 1 else None)
+    sim.seed_infections(seeds[np.isin(seeds, idx)])
     sim.step(6 * a.days)
 
     ora = OracleModel(pop, dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob), tab, 4242)
@@ -59,14 +70,13 @@ def main():
         ora.step()
 
     got, want = sim.state(), ora.state_dict()
-    hh_off = int(pop.household[lo])
     D = spec.n_districts
     bad = []
     for key in STATE_KEYS:
         g = np.asarray(got[key]).astype(np.int64)
-        w = want[key][lo:hi].astype(np.int64)
+        w = want[key][idx].astype(np.int64)
         if key in ('current_location_ids', 'infected_at_location_ids'):
-            g = np.where(g >= D, g + hh_off, g)          # shard-local household numbering -> global
+            g = np.where(g >= D, pop.household[idx] + D, g)          # shard-local household numbering -> global
         if not np.array_equal(g, w):
             bad.append((key, int((g != w).sum())))
     rows = distributed.sum_over_ranks(sim.read_log()[:, :12].copy(), device)
@@ -84,7 +94,7 @@ def main():
     flag = torch.tensor([len(bad)], device=device)
     if world > 1:
         dist.all_reduce(flag)
-    print(f'rank {rank}/{world}: agents [{lo}, {hi}) infected {int((want["epidemic_state"][lo:hi] > 0).sum())} '
+    print(f'rank {rank}/{world}: {idx.shape[0]} agents in [{lo}, {hi}) ({a.shards}) infected {int((want["epidemic_state"][idx] > 0).sum())} '
           f'mismatches {bad}', flush=True)
     failed = int(flag.item()) != 0
     if rank == 0 and not failed:

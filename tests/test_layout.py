@@ -120,3 +120,39 @@ def test_slot_map_properties_on_random_households():
                 assert len(set(zip(hh_here.tolist(), ix_here.tolist()))) == len(set(hh_here.tolist())) == len(set(ix_here.tolist()))
 
     check()
+
+
+def test_slot_map_of_a_dealt_shard():
+    """A shard made of one piece of every district (sharding.deal_population): per-agent global ids, a new sub-tile at
+    every id run, slot offset o still holds id base + o with base % 4 == 0, big households keep their global start."""
+    from abm_b200 import sharding
+    spec = synth.make_spec(n_districts=7, seed=4)
+    pop = synth.make_population(30_000, spec, seed=4)
+    hh = pop.household.copy()
+    hh[12_000:12_150] = hh[12_000]                  # a camp-sized household inside some district
+    _, hh = np.unique(hh, return_inverse=True)
+    pop.household = hh.astype(np.int64)
+    S = C.SUBTILE
+    whole = layout.build_slot_map(pop.household, pop.district)
+    covered = np.zeros(pop.n, dtype=int)
+    for world in (2, 3):
+        for idx in sharding.deal_population(pop, world):
+            shard = sharding.take_population(pop, idx)
+            assert np.array_equal(np.unique(shard.district), np.arange(7))            # a piece of every district
+            sm = layout.build_slot_map(shard.household, shard.district, agent_ids=idx)
+            sub = sm.slot_of // S
+            sub_base = (sm.sub_info & np.uint64((1 << 48) - 1)).astype(np.int64)
+            assert np.all(sub_base % 4 == 0)
+            assert np.array_equal(sub_base[sub] + sm.slot_of % S, idx)
+            assert np.array_equal((sm.sub_info >> np.uint64(48)).astype(np.int64)[sub], shard.district)
+            sizes = np.bincount(shard.household)
+            head = np.r_[True, shard.household[1:] != shard.household[:-1]]
+            small = sizes[shard.household] <= C.BIG_HOUSEHOLD
+            assert np.all(sub[small] == sub[head][shard.household][small])
+            # households are never cut by the deal, and the camp keeps its global first id
+            assert pop.household[idx[0]] != pop.household[idx[0] - 1] if idx[0] else True
+            if sm.big_size.size:
+                assert sm.big_size.tolist() == [150] and sm.big_start[0] == whole.big_start[0]
+            if world == 2:
+                covered[idx] += 1
+    assert np.all(covered == 1)

@@ -12,14 +12,15 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('exchange', ['p2p', 'nccl'])
-def test_two_ranks_match_single_rank_oracle(built_library, exchange):
+@pytest.mark.parametrize('exchange,shards', [('p2p', 'contiguous'), ('nccl', 'contiguous'), ('p2p', 'dealt')])
+def test_two_ranks_match_single_rank_oracle(built_library, exchange, shards):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
+    port = {('p2p', 'contiguous'): '29533', ('nccl', 'contiguous'): '29534', ('p2p', 'dealt'): '29535'}[(exchange, shards)]
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
-           '127.0.0.1', '--master-port', '29533' if exchange == 'p2p' else '29534', os.path.join(ROOT, 'tests', 'multi_gpu_check.py'),
-           '--agents', '80000', '--days', '12', '--exchange', exchange]
+           '127.0.0.1', '--master-port', port, os.path.join(ROOT, 'tests', 'multi_gpu_check.py'),
+           '--agents', '80000', '--days', '12', '--exchange', exchange, '--shards', shards]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'multi_gpu_check ok' in res.stdout
