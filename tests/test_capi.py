@@ -76,3 +76,12 @@ def test_null_handles_are_argument_errors(built_library):
     assert lib.abm_peer_export(None, None) == -1 and lib.abm_peer_attach(None, None, 0) == -1
     assert lib.abm_nccl_unique_id(None) == -1
     lib.abm_destroy(None)          # a no-op, like free(NULL)
+
+
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md maps each C entry point to the reference interface it replaces: none may be missing."""
+    header = open(os.path.join(ROOT, 'include', 'abm_b200.h')).read()
+    declared = set(re.findall(r'\b(abm_[a-z_]+)\s*\(', header))
+    guide = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    mentioned = set(re.findall(r'\babm_[a-z_]+\b', guide))
+    assert declared - mentioned == set(), sorted(declared - mentioned)
