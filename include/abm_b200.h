@@ -167,11 +167,17 @@ int abm_table_time(abm_handle* h, double* total_ms);
  * and the number of seeded infections.  abm_get_state applies pending draws first (abm_flush). */
 int abm_get_state(abm_handle* h, int64_t* k, int64_t counters[ABM_N_COUNTERS], int64_t* seeded);
 int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTERS], int64_t seeded);
+/* scheduler.steps (base_model.py:177): sub-steps enqueued so far. */
 int64_t abm_current_step(abm_handle* h);
+/* Kernels launched by this handle so far (graph replays count their nodes); for bench.py's `gpu_launches`. */
 int64_t abm_launch_count(abm_handle* h);
+/* Wait for everything enqueued on the handle's stream (the reference's step() is synchronous; abm_step is not). */
 int abm_sync(abm_handle* h);
+/* Message of the last failed call on this handle (every entry point returns 0 or a negative abm_status). */
 const char* abm_last_error(abm_handle* h);
+/* Frees what the library owns (tables, accumulators, graph, communicator); never the caller's agent buffers. */
 void abm_destroy(abm_handle* h);
+/* ABI version, major * 100 + minor. */
 int abm_version(void);
 /* ncclGetUniqueId into a 128-byte buffer (rank 0 calls it and broadcasts the bytes out of band). */
 int abm_nccl_unique_id(void* out128);
