@@ -36,6 +36,9 @@ CASES = {
     'accelerated_schools_100k': ('AcceleratedGovernmentOpenSchoolsScenario', 100_000, 60, 45, 200, 32, 1.9),
     'isolate_symptomatic_100k': ('IsolateSymptomaticScenario', 100_000, 60, 45, 200, 32, 1.9),
     'handwashing_risk_100k': ('HandWashingRiskScenario', 100_000, 60, 45, 200, 32, 1.9),
+    # round 2: the same two headline scenarios THROUGH THE PEAK and the decline (the 45-day windows above stop before it)
+    'unmitigated_100k_120d': ('UnmitigatedScenario', 100_000, 60, 120, 200, 32, 1.9),
+    'open_manufacturing_schools_100k_120d': ('OpenManufacturingAndSchoolsScenario', 100_000, 60, 120, 200, 32, 1.9),
 }
 MINING_SHARE = 0.15
 POP_SEED = 2020
@@ -59,7 +62,7 @@ def member(args):
     start = datetime(2020, 9, 1, 0)
     spec = synth.make_spec(n_districts=D, R0=R0, seed=POP_SEED, start_datetime=start)
     pop = synth.make_population(n_agents, spec, seed=POP_SEED, scenario_flags=True)
-    if case in ('selective_lockdown_100k', 'open_manufacturing_schools_100k'):
+    if case in ('selective_lockdown_100k', 'open_manufacturing_schools_100k', 'open_manufacturing_schools_100k_120d'):
         pop = scenario_columns(pop, D)
     if case == 'open_mining_100k':
         pop.extras['mining_district_id'] = synth.mining_camp_column(pop, D, POP_SEED, MINING_SHARE)
@@ -92,7 +95,7 @@ def member(args):
 def main(names):
     for case in names:
         scenario, n_agents, D, days, infect_num, members, R0 = CASES[case]
-        with mp.Pool(min(8, os.cpu_count())) as pool:
+        with mp.Pool(min(int(os.environ.get('REF_PROCS', '8')), os.cpu_count())) as pool:
             res = pool.map(member, [(case, m) for m in range(members)], chunksize=1)
         keys = [k for k in res[0]['rows'][0] if k != 'date']
         data = {k: [[r[k] for r in x['rows']] for x in res] for k in keys}
@@ -102,7 +105,7 @@ def main(names):
                    dates=[r['date'] for r in res[0]['rows']], counters=data,
                    reference_seconds_per_member=float(np.mean(run_s)),
                    reference_agent_days_per_s_1core=float(n_agents * days / np.mean(run_s)),
-                   note='timings taken with 8 members running concurrently on 8 vCPUs')
+                   note=f"timings taken with {os.environ.get('REF_PROCS', '8')} members running concurrently on 8 vCPUs")
         with open(os.path.join(HERE, f'ref_ensemble_{case}.json'), 'w') as fl:
             json.dump(out, fl)
         act = np.array(data['current_contagious_cases'])
