@@ -248,6 +248,7 @@ def run_cuda_arm(a):
     prof_days = max(1, min(a.steps, 5))
     sim.step(prof_days * SUBSTEPS_PER_DAY)
     kms, klaunches = sim.kernel_time()
+    ems, tms = sim.event_time(), sim.table_time()
     sim.set_profiling(False)
     peaks = {}
     try:
@@ -265,8 +266,9 @@ def run_cuda_arm(a):
         except Exception:
             traffic = None
     roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
-                    kernel='abm_substep_kernel', avg_launch_ms=kms / klaunches, launches_timed=klaunches,
+                    kernel='abm_sweep_kernel', avg_launch_ms=kms / klaunches, launches_timed=klaunches,
                     algorithmic_bytes_per_launch=per_launch_bytes,
+                    event_kernel_avg_ms=ems / klaunches, table_kernel_avg_ms=tms / klaunches,
                     peak_source='MEASURED_PEAKS.json (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                     own_layout_bytes_per_launch=8.0 * sim.sm.n_slots,
                     whole_day_frac=ALGO_BYTES_PER_AGENT_DAY * pop.n / (ms / a.steps * 1e-3) / 1e9 / peak)

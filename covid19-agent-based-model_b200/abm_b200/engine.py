@@ -45,14 +45,17 @@ class AbmTables(ct.Structure):
 
 
 class AbmAgentPtrs(ct.Structure):
-    _fields_ = [(n, ct.c_void_p) for n in
-                ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
-                 'move_class', 'econ_pool', 'hh_index')]
+    _fields_ = [(n, ct.c_void_p) for n in ('flags', 'aux', 'cold', 'move_class', 'econ_pool', 'hh_index')]
+
+
+# words of an agent's cold record (include/abm_b200.h ABM_COLD_*): one 32-byte sector per agent
+COLD_WORDS = 8
+COLD_FIELDS = ('t_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at')
 
 
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
            'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
-           'abm_kernel_time', 'abm_table_time', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
+           'abm_kernel_time', 'abm_table_time', 'abm_event_time', 'abm_set_trace', 'abm_read_trace', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
            'abm_version', 'abm_nccl_unique_id', 'abm_peer_export', 'abm_peer_attach', 'abm_peer_detach']
 
 _lib = None
@@ -84,6 +87,9 @@ def load_library(path=LIB_PATH):
     lib.abm_set_profiling.argtypes = [vp, ct.c_int32]
     lib.abm_kernel_time.argtypes = [vp, ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
     lib.abm_table_time.argtypes = [vp, ct.POINTER(ct.c_double)]
+    lib.abm_event_time.argtypes = [vp, ct.POINTER(ct.c_double)]
+    lib.abm_set_trace.argtypes = [vp, ct.c_int32]
+    lib.abm_read_trace.argtypes = [vp, vp, ct.c_int32]
     lib.abm_get_state.argtypes = [vp, ct.POINTER(ct.c_int64), vp, ct.POINTER(ct.c_int64)]
     lib.abm_set_state.argtypes = [vp, ct.c_int64, vp, ct.c_int64]
     lib.abm_current_step.argtypes = [vp]
@@ -129,12 +135,10 @@ class HostStore:
             out[sm.slot_of] = values
             return out
 
-        never = np.int32(C.T_NEVER)
+        cold = np.zeros((n_slots, COLD_WORDS), np.int32)
+        cold[:, :5] = np.int32(C.T_NEVER)      # the five dates are datetime.max; inf_at and the padding are 0
         arrays = dict(
-            flags=flags.view(np.int32), aux=aux.view(np.int32),
-            t_infected=np.full(n_slots, never, np.int32), t_contagious=np.full(n_slots, never, np.int32),
-            t_onset=np.full(n_slots, never, np.int32), t_recovered=np.full(n_slots, never, np.int32),
-            t_return=np.full(n_slots, never, np.int32), inf_at=np.zeros(n_slots, np.int32),
+            flags=flags.view(np.int32), aux=aux.view(np.int32), cold=cold,
             move_class=slots_from_agents(self.move_class, 0, np.uint16).view(np.int16),
             hh_index=layout.household_index(flags),
         )
@@ -249,8 +253,7 @@ class Simulation:
             setattr(at, name, _ptr(arr))
         self._check(self.lib.abm_set_tables(self.h, ct.byref(at)))
         ap = AbmAgentPtrs()
-        for name in ('flags', 'aux', 't_infected', 't_contagious', 't_onset', 't_recovered', 't_return', 'inf_at',
-                     'move_class', 'hh_index'):
+        for name in ('flags', 'aux', 'cold', 'move_class', 'hh_index'):
             setattr(ap, name, self.buf[name].data_ptr())
         ap.econ_pool = self.buf['econ_pool'].data_ptr() if 'econ_pool' in self.buf else None
         self._check(self.lib.abm_bind_agents(self.h, ct.byref(ap)))
@@ -359,7 +362,11 @@ class Simulation:
         out = {}
         for k, v in self.buf.items():
             a = v.cpu().numpy()
-            if k in ('flags', 'aux', 'inf_at'):
+            if k == 'cold':                    # split the record into the per-field vectors layout.unpack_state reads
+                for j, name in enumerate(COLD_FIELDS):
+                    out[name] = np.ascontiguousarray(a[:, j]).view(np.uint32 if name == 'inf_at' else np.int32)
+                continue
+            if k in ('flags', 'aux'):
                 a = a.view(np.uint32)
             elif k == 'move_class':
                 a = a.view(np.uint16)
@@ -403,6 +410,21 @@ class Simulation:
     def table_time(self):
         ms = ct.c_double()
         self._check(self.lib.abm_table_time(self.h, ct.byref(ms)))
+        return ms.value
+
+    def set_trace(self, n_substeps):
+        """Device-side timeline of sub-steps 0..n-1 (abm_set_trace); 0 switches it off."""
+        self._check(self.lib.abm_set_trace(self.h, int(n_substeps)))
+
+    def read_trace(self, n_substeps):
+        """uint64 [n, 3 kernels (sweep, events, table), 2 (first CTA start, last CTA end)] in ns of the GPU timer."""
+        out = np.zeros((int(n_substeps), 3, 2), dtype=np.uint64)
+        self._check(self.lib.abm_read_trace(self.h, _ptr(out), int(n_substeps)))
+        return out
+
+    def event_time(self):
+        ms = ct.c_double()
+        self._check(self.lib.abm_event_time(self.h, ct.byref(ms)))
         return ms.value
 
     @property

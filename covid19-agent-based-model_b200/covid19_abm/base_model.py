@@ -95,7 +95,7 @@ class EpidemicScheduler:
 
     # ---- the pieces of the reference's step are phases of one fused kernel here
     def _fused(self, name):
-        raise NotImplementedError(f'EpidemicScheduler.{name} is a phase of abm_substep_kernel (csrc/abm_kernels.cuh) and '
+        raise NotImplementedError(f'EpidemicScheduler.{name} is a phase of abm_sweep_kernel (csrc/abm_kernels.cuh) and '
                                   'cannot be run on its own; call step()')
 
     def update_agent_states(self):

@@ -48,6 +48,13 @@ struct abm_handle {
     unsigned long long* xchg[ABM_MAX_RANKS] = {};      // every rank's buffer as mapped in this process
     bool peers_attached = false;
     unsigned int* rows_done = nullptr;
+    uint4* q_entries = nullptr;         // event queues (see DevWork)
+    uint32_t* q_count = nullptr;
+    uint32_t q_mask = 0, q_cap = 0;
+    unsigned long long* scratch = nullptr;   // [2 * D + 8] words for the read-back kernels (abm_counters, abm_district_symptomatic)
+    unsigned long long* trace = nullptr;     // optional timeline (abm_set_trace)
+    int32_t trace_rows = 0;
+    bool exchange_failed = false;       // sticky: a peer did not publish its table rows in time
     int32_t replicas = 1;
     uint32_t* thr_out = nullptr;        // [P][A]
     unsigned long long* hbig[2] = {nullptr, nullptr};
@@ -78,6 +85,9 @@ struct abm_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_table_events;   // around the table kernel(s) of a sub-step
     size_t prof_table_used = 0;
     double prof_table_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_event_events;   // around the event kernel of a sub-step
+    size_t prof_event_used = 0;
+    double prof_event_ms = 0.0;
     int64_t launches = 0;
     // NCCL
     void* nccl_lib = nullptr;
@@ -154,6 +164,8 @@ DevWork make_work(const abm_handle* h) {
     w.rep_mask = (uint32_t)h->replicas - 1u;
     w.max_log_rows = h->cfg.max_log_rows;
     w.rows_done = h->rows_done;
+    w.trace = h->trace; w.trace_rows = h->trace_rows;
+    w.q_entries = h->q_entries; w.q_count = h->q_count; w.q_mask = h->q_mask; w.q_cap = h->q_cap;
     w.n_ranks = 1; w.rank = 0;
     if (h->peers_attached) {
         w.n_ranks = h->cfg.world_size; w.rank = h->cfg.rank;
@@ -162,33 +174,49 @@ DevWork make_work(const abm_handle* h) {
     return w;
 }
 
+int timed_pair(abm_handle* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& pool, size_t& used, cudaEvent_t* e0, cudaEvent_t* e1) {
+    if (used == pool.size()) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CUDA_TRY(h, cudaEventCreate(&a));
+        CUDA_TRY(h, cudaEventCreate(&b));
+        pool.emplace_back(a, b);
+    }
+    *e0 = pool[used].first;
+    *e1 = pool[used].second;
+    used++;
+    return ABM_OK;
+}
+
+// The agent part of a sub-step: the sweep over every slot, then the event kernel over the agents it deferred.
 int launch_main(abm_handle* h, uint32_t mode) {
     const DevWork w = make_work(h);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, v0 = nullptr, v1 = nullptr;
     if (h->profiling) {
-        if (h->prof_used == h->prof_events.size()) {
-            CUDA_TRY(h, cudaEventCreate(&e0));
-            CUDA_TRY(h, cudaEventCreate(&e1));
-            h->prof_events.emplace_back(e0, e1);
-        }
-        e0 = h->prof_events[h->prof_used].first;
-        e1 = h->prof_events[h->prof_used].second;
-        h->prof_used++;
+        int rc = timed_pair(h, h->prof_events, h->prof_used, &e0, &e1);
+        if (rc) return rc;
+        if ((rc = timed_pair(h, h->prof_event_events, h->prof_event_used, &v0, &v1))) return rc;
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
     const dim3 grid((unsigned)(h->cfg.n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS)), block(THREADS);    // one warp per sub-tile
     uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
-    const uint32_t rt_bits = (mode & M_STEP) ? 0u : M_NO_EARLY_DEPENDENTS;   // a flush is followed by a sub-step kernel, not a table kernel
+    const bool pdl = h->cfg.use_pdl != 0;
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
-#define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_substep_kernel<MODE>, grid, block, h->stream, h->cfg.use_pdl != 0, h->T, h->G, w, (const DevClock*)h->clock, m | rt_bits))
+#define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_sweep_kernel<MODE>, grid, block, h->stream, pdl, h->T, h->G, w, (const DevClock*)h->clock, m))
     if (m == (M_INFECT | M_STEP | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_INCR);                       // night
     else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR);   // day
     else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
     else if (m == (M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_HOME | M_DENSE_I);
-    else if (m == M_INFECT) ABM_LAUNCH(M_INFECT);                                                       // abm_flush
     else ABM_LAUNCH(RUNTIME_MODE);
 #undef ABM_LAUNCH
-    if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+    if (h->profiling) {
+        CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+        CUDA_TRY(h, cudaEventRecord(v0, h->stream));
+    }
+    // a flush is followed by a sweep (which reads the agent store before its dependency wait), not by a table kernel
+    const uint32_t rt_bits = (mode & M_STEP) ? 0u : M_NO_EARLY_DEPENDENTS;
+    CUDA_TRY(h, launch_pdl(abm_event_kernel, dim3(h->q_mask + 1u), dim3(EVENT_THREADS), h->stream, pdl, h->T, h->G, w,
+                           (const DevClock*)h->clock, m | rt_bits));
+    if (h->profiling) CUDA_TRY(h, cudaEventRecord(v1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return ABM_OK;
 }
@@ -227,14 +255,7 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
     ta.incremental = (p.mode & M_INCR) ? 1 : 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->profiling) {
-        if (h->prof_table_used == h->prof_table_events.size()) {
-            CUDA_TRY(h, cudaEventCreate(&t0));
-            CUDA_TRY(h, cudaEventCreate(&t1));
-            h->prof_table_events.emplace_back(t0, t1);
-        }
-        t0 = h->prof_table_events[h->prof_table_used].first;
-        t1 = h->prof_table_events[h->prof_table_used].second;
-        h->prof_table_used++;
+        if ((rc = timed_pair(h, h->prof_table_events, h->prof_table_used, &t0, &t1))) return rc;
         CUDA_TRY(h, cudaEventRecord(t0, h->stream));
     }
     if (c.world_size > 1 && c.exchange == 1 && !h->peers_attached)
@@ -246,11 +267,11 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
         if (r != ncclSuccess) return fail(h, ABM_ERR_NCCL, "ncclAllReduce: %s", h->nccl_errstr ? h->nccl_errstr(r) : "?");
         ta.do_reduce = 0; ta.do_threshold = 1;
         CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools + 1), dim3(TABLE_THREADS), h->stream, false, h->T, w, h->clock, ta));
-        *launches += 3;
+        *launches += 4;
     } else {
         ta.do_reduce = 1; ta.do_threshold = 1;
         CUDA_TRY(h, launch_pdl(abm_hazard_table_kernel, dim3(c.n_pools + 1), dim3(TABLE_THREADS), h->stream, c.use_pdl != 0, h->T, w, h->clock, ta));
-        *launches += 2;
+        *launches += 3;
     }
     if (h->profiling) CUDA_TRY(h, cudaEventRecord(t1, h->stream));
     CUDA_TRY(h, cudaGetLastError());
@@ -317,6 +338,12 @@ int collect_profile(abm_handle* h) {
         h->prof_table_ms += ms;
     }
     h->prof_table_used = 0;
+    for (size_t i = 0; i < h->prof_event_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->prof_event_events[i].first, h->prof_event_events[i].second));
+        h->prof_event_ms += ms;
+    }
+    h->prof_event_used = 0;
     return ABM_OK;
 }
 
@@ -324,7 +351,7 @@ int collect_profile(abm_handle* h) {
 
 extern "C" {
 
-int abm_version(void) { return 100; }
+int abm_version(void) { return 200; }
 
 int abm_nccl_unique_id(void* out128) {
     if (!out128) return ABM_ERR_ARG;
@@ -381,6 +408,21 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if ((rc = alloc_zero(h, (size_t)12, &h->counters))) return rc;
     if ((rc = alloc_zero(h, (size_t)1, &h->clock))) return rc;
     if ((rc = alloc_zero(h, (size_t)1, &h->rows_done))) return rc;
+    if ((rc = alloc_zero(h, (size_t)2 * cfg->n_districts + 8, &h->scratch))) return rc;
+    {
+        // event queues: a power of two <= 2048 of them; queue q takes the events of the sweep CTAs b with
+        // b & q_mask == q, so its worst case (every agent of those CTAs deferred) is ceil(n_ctas / n_queues) tiles
+        const int64_t n_ctas = cfg->n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS;
+        uint32_t nq = 1;
+        while (nq < 2048u && (int64_t)nq * 2 <= n_ctas) nq <<= 1;
+        h->q_mask = nq - 1u;
+        h->q_cap = (uint32_t)(((n_ctas + nq - 1) / nq) * (WARPS * ABM_SUBTILE));
+        if ((rc = alloc_zero(h, (size_t)nq, &h->q_count))) return rc;
+        uint4* qe = nullptr;
+        CUDA_TRY(h, cudaMalloc(&qe, (size_t)nq * h->q_cap * sizeof(uint4)));
+        h->owned.push_back(qe);
+        h->q_entries = qe;
+    }
     {
         DevClock clk{};
         clk.k = 0; clk.now = 0; clk.minute_abs = cfg->start_minute_of_day; clk.weekday0 = cfg->start_weekday;
@@ -457,14 +499,13 @@ int abm_set_tables(abm_handle* h, const abm_tables* t) {
 
 int abm_bind_agents(abm_handle* h, const abm_agent_ptrs* dev) {
     if (!h || !dev) return ABM_ERR_ARG;
-    if (!dev->flags || !dev->aux || !dev->t_infected || !dev->t_contagious || !dev->t_onset || !dev->t_recovered ||
-        !dev->t_return || !dev->inf_at || !dev->move_class || !dev->hh_index)
+    if (!dev->flags || !dev->aux || !dev->cold || !dev->move_class || !dev->hh_index)
         return fail(h, ABM_ERR_ARG, "null agent buffer");
+    if ((uintptr_t)dev->cold & 31) return fail(h, ABM_ERR_ARG, "cold records must be 32-byte aligned");
     if (((uintptr_t)dev->flags | (uintptr_t)dev->aux) & 15) return fail(h, ABM_ERR_ARG, "flags/aux must be 16-byte aligned");
     if (((uintptr_t)dev->move_class & 7) || ((uintptr_t)dev->hh_index & 3)) return fail(h, ABM_ERR_ARG, "move_class / hh_index misaligned");
     DevAgents& G = h->G;
-    G.flags = dev->flags; G.aux = dev->aux; G.t_infected = dev->t_infected; G.t_contagious = dev->t_contagious;
-    G.t_onset = dev->t_onset; G.t_recovered = dev->t_recovered; G.t_return = dev->t_return; G.inf_at = dev->inf_at;
+    G.flags = dev->flags; G.aux = dev->aux; G.cold = dev->cold;
     G.move_class = dev->move_class; G.econ_pool = dev->econ_pool;
     G.hh_index = reinterpret_cast<const uint32_t*>(dev->hh_index);
     h->have_agents = true;
@@ -562,7 +603,7 @@ int abm_flush(abm_handle* h) {
     if (!h->pending_infect) return ABM_OK;
     int rc = launch_main(h, M_INFECT | (h->daytime ? M_DENSE_I : 0u));
     if (rc) return rc;
-    h->launches++;
+    h->launches += 2;
     h->pending_infect = false;
     return ABM_OK;
 }
@@ -663,6 +704,7 @@ int abm_set_profiling(abm_handle* h, int32_t on) {
     h->prof_ms = 0.0;
     h->prof_launches = 0;
     h->prof_table_ms = 0.0;
+    h->prof_event_ms = 0.0;
     return ABM_OK;
 }
 
@@ -778,6 +820,36 @@ int abm_table_time(abm_handle* h, double* total_ms) {
     return ABM_OK;
 }
 
+int abm_set_trace(abm_handle* h, int32_t n_substeps) {
+    if (!h || n_substeps < 0) return ABM_ERR_ARG;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }     // kernel arguments change
+    if (h->trace) { cudaFree(h->trace); h->trace = nullptr; h->trace_rows = 0; }
+    if (n_substeps == 0) return ABM_OK;
+    const size_t words = (size_t)n_substeps * 6;
+    CUDA_TRY(h, cudaMalloc(&h->trace, words * sizeof(unsigned long long)));
+    std::vector<unsigned long long> init(words);
+    for (size_t i = 0; i < words; ++i) init[i] = (i & 1) ? 0ull : ~0ull;        // [min start, max end]
+    CUDA_TRY(h, cudaMemcpy(h->trace, init.data(), words * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    h->trace_rows = n_substeps;
+    return ABM_OK;
+}
+
+int abm_read_trace(abm_handle* h, uint64_t* out, int32_t n_substeps) {
+    if (!h || !out || n_substeps < 0 || n_substeps > h->trace_rows) return ABM_ERR_ARG;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(out, h->trace, (size_t)n_substeps * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return ABM_OK;
+}
+
+int abm_event_time(abm_handle* h, double* total_ms) {
+    if (!h || !total_ms) return ABM_ERR_ARG;
+    int rc = collect_profile(h);
+    if (rc) return rc;
+    *total_ms = h->prof_event_ms;
+    return ABM_OK;
+}
+
 int64_t abm_current_step(abm_handle* h) { return h ? h->k : -1; }
 int64_t abm_launch_count(abm_handle* h) { return h ? h->launches : -1; }
 
@@ -791,7 +863,9 @@ void abm_destroy(abm_handle* h) {
     if (h->comm && h->nccl_destroy) h->nccl_destroy(h->comm);
     for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : h->prof_table_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto& p : h->prof_event_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     abm_peer_detach(h);
+    if (h->trace) cudaFree(h->trace);
     if (h->xchg_self) cudaFree(h->xchg_self);
     for (void* p : h->owned) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

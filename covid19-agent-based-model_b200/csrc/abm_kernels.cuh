@@ -102,9 +102,16 @@ struct DevTables {
 
 struct DevAgents {
     uint32_t* flags; uint32_t* aux;
-    int32_t* t_infected; int32_t* t_contagious; int32_t* t_onset; int32_t* t_recovered; int32_t* t_return;
-    uint32_t* inf_at; const uint16_t* move_class; const uint32_t* econ_pool; const uint32_t* hh_index;
+    int32_t* cold;      // [n_slots][ABM_COLD_WORDS]: one 32-byte sector per agent (ABM_COLD_* word indices)
+    const uint16_t* move_class; const uint32_t* econ_pool; const uint32_t* hh_index;
 };
+// the cold record as two 16-byte halves
+struct Cold { int4 t; int4 u; };    // t = (t_infected, t_contagious, t_onset, t_recovered), u = (t_return, inf_at, 0, 0)
+__device__ __forceinline__ Cold load_cold(const DevAgents& G, uint32_t slot) {
+    const int4* p = reinterpret_cast<const int4*>(G.cold) + (size_t)slot * 2;
+    Cold c; c.t = p[0]; c.u = p[1];
+    return c;
+}
 
 // Accumulators that every CTA adds to exist in `rep_mask + 1` replicas (a CTA uses replica
 // blockIdx & rep_mask): atomics on one address serialise in L2, and the hottest rows (the capital's
@@ -125,6 +132,13 @@ struct DevWork {
     // that its peers map; layout in 64-bit words: data [2 parities][2][P][A], then 32-bit flags [2 parities][P]
     unsigned long long* xchg[ABM_MAX_RANKS];   // xchg[r] = rank r's buffer as mapped here (own buffer at index `rank`)
     unsigned int* rows_done;        // table-kernel rows finished in the current launch
+    // event queues: sweep CTA b appends to queue b & q_mask; queue q owns entries [q * q_cap, (q + 1) * q_cap)
+    uint4* q_entries;               // (slot | newly-infected << 31, flags, aux, 0)
+    uint32_t* q_count;              // [q_mask + 1] entries used; reset by the event kernel
+    uint32_t q_mask, q_cap;
+    // optional timeline (abm_set_trace): [sub-step k][kernel 0 sweep / 1 events / 2 table][0 first CTA start, 1 last CTA end], ns
+    unsigned long long* trace;
+    int32_t trace_rows;
     int32_t n_ranks, rank;          // n_ranks > 1 only when the peer exchange is active
 };
 
@@ -144,6 +158,21 @@ struct __align__(16) DevClock {
     int32_t xchg_error;       // a peer did not publish its rows in time
 };
 
+// Loads of what the PRECEDING grid wrote (thresholds, clock), issued after grid_dependency_wait: the default cached
+// load (ld.global.ca).  The wait makes the predecessor's stores visible to these; ld.global.nc (__ldg) would be wrong
+// here (the data is not read-only for the lifetime of this grid) and ld.global.cg would send every look-up of the
+// small threshold table to L2.
+__device__ __forceinline__ uint32_t ld_ca(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 ld_ca(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.ca.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 struct StepArgs {
     int32_t k;        // sub-step being executed (T/M/A phases)
     int32_t now;      // its minute tick
@@ -152,8 +181,8 @@ struct StepArgs {
     uint32_t mode;
     int32_t weekday;  // 0..6 of `now`
 };
-__device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock* __restrict__ clk, uint32_t mode) {
-    const int4 c = __ldg(reinterpret_cast<const int4*>(clk));           // k, now, weekday, minute_abs
+__device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock* clk, uint32_t mode) {
+    const int4 c = ld_ca(reinterpret_cast<const int4*>(clk));           // k, now, weekday, minute_abs (written by the table kernel)
     StepArgs s;
     s.k = c.x; s.now = c.y; s.k_inf = s.k - 1; s.now_inf = s.now - T.step_ticks;
     s.weekday = c.z;
@@ -168,6 +197,20 @@ __device__ __forceinline__ StepArgs step_args(const DevTables& T, const DevClock
 // predecessor has completed and its memory is visible.  Both are no-ops for a normally serialised launch.
 __device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread per CTA stamps the launch's [first start, last end] window
+__device__ __forceinline__ void trace_stamp(const DevWork& Wk, int k, int kernel, unsigned long long t_start) {
+    if (Wk.trace && threadIdx.x == 0 && k >= 0 && k < Wk.trace_rows) {
+        unsigned long long* row = Wk.trace + ((size_t)k * 3 + kernel) * 2;
+        atomicMin(row, t_start);
+        atomicMax(row + 1, global_timer_ns());
+    }
+}
 
 // system-scope accesses for memory shared with peer GPUs
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -290,7 +333,8 @@ __device__ __forceinline__ int pool_of(const DevAgents& G, uint32_t f, uint32_t 
 // location an agent that goes about its economic activity ends up in (base_model.py:331-339, 346-352)
 __device__ __forceinline__ uint32_t econ_loc(uint32_t f) {
     const uint32_t ek = (f >> F_EKIND_SHIFT) & F_EKIND_MASK;
-    return ek == EKIND_HOME_DISTRICT ? LOC_HOMEPOOL : (ek == EKIND_HOUSEHOLD ? LOC_HOME : LOC_POOL);
+    static_assert(EKIND_HOUSEHOLD == 0 && LOC_HOME == 0 && EKIND_HOME_DISTRICT == 1 && LOC_HOMEPOOL == 1 && EKIND_POOL == 2 && LOC_POOL == 3, "econ_loc");
+    return ek + (ek >> 1);          // branch-free: no jump table in the middle of divergent code
 }
 // get_active_ids (base_model.py:198-209): (not hospitalised, or recovered) and at a non-negative location.
 // The location test is implied: hospital / dead locations only occur with clinical state >= 1 and an
@@ -304,8 +348,8 @@ __device__ __forceinline__ bool is_active(uint32_t f) {
 // cold vectors; the high half of `a` gets the sub-step at which the first scheduled event fires (>= k_first).
 // tally: shared (int) or global (unsigned long long) array indexed by the enum above.
 template <typename TallyT>
-__device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
-                                                 int64_t cid, int32_t k_inf, int32_t now_inf, uint32_t k_first, TallyT* tally) {
+__device__ __forceinline__ uint32_t infect_agent(const DevTables& T, uint32_t f, uint32_t& a, Cold& c, int64_t cid, int32_t k_inf,
+                                                 int32_t now_inf, uint32_t k_first, TallyT* tally) {
     const U4 A4 = agent_draws(T, cid, k_inf, SITE_COURSE_A);
     const U4 B4 = agent_draws(T, cid, k_inf, SITE_COURSE_B);
     const uint32_t age = (f >> F_AGE_SHIFT) & F_AGE_MASK;
@@ -336,11 +380,8 @@ __device__ __forceinline__ uint32_t infect_agent(const DevTables& T, const DevAg
         atomicAdd(tally + CUM_ASYM, (TallyT)1);
     }
     atomicAdd(tally + PRE_EXPOSED, (TallyT)1);
-    __stcs(G.t_infected + slot, now_inf);                                                   // :851
-    __stcs(G.t_contagious + slot, t_c);
-    __stcs(G.t_onset + slot, t_o);
-    __stcs(G.t_recovered + slot, t_r);
-    __stcs(G.inf_at + slot, (loc_of(f) << 16) | cur);                                       // :846-847
+    c.t = make_int4(now_inf, t_c, t_o, t_r);                                                // :851
+    c.u.y = (int32_t)((loc_of(f) << 16) | cur);                                             // :846-847
     f &= ~(F_EPI_MASK | F_SYMPT | F_ASYMPT | F_OUT_H | F_OUT_C | F_OUT_D | F_ONSET);
     f |= EPI_I | (sym ? F_SYMPT : F_ASYMPT) | out;                                          // :850
     // earliest scheduled event: the one with the smallest date (fire_index is monotone)
@@ -371,9 +412,9 @@ struct DeltaSink {          // where incremental sub-steps send their table chan
 };
 
 __device__ __forceinline__ uint32_t transition_agent(const DevTables& T, const DevAgents& G, uint32_t f, uint32_t& a, uint32_t slot,
-                                                     int32_t now, int* s_tally, const DeltaSink* sink = nullptr) {
+                                                     const Cold& c, int32_t now, int* s_tally, const DeltaSink* sink = nullptr) {
     const uint32_t f_before = f;
-    const int32_t t_c = __ldcs(G.t_contagious + slot), t_o = __ldcs(G.t_onset + slot), t_r = __ldcs(G.t_recovered + slot);
+    const int32_t t_c = c.t.y, t_o = c.t.z, t_r = c.t.w;
     const int32_t t_h = (f & F_OUT_H) ? t_o + 5 * DAY : T_NEVER;    // params.py:165
     const int32_t t_cs = (f & F_OUT_C) ? t_o + 13 * DAY : T_NEVER;  // hospital end = critical start (base_model.py:953)
     const int32_t t_d = (f & F_OUT_D) ? t_o + 21 * DAY : T_NEVER;   // params.py:177 (== end of critical care when critical)
@@ -457,21 +498,48 @@ __device__ __forceinline__ int32_t stay_return_tick(const DevTables& T, uint32_t
 }
 
 // first column j with u < thr[j] of a non-decreasing OD row; none -> column 0 (quirk Q8)   base_model.py:372-377
+// 8-ary search: the pivots of a level are independent loads, so a row of 60 columns costs two memory round trips
+// (500 columns: three) instead of the six to nine dependent ones of a binary search.
 __device__ __forceinline__ uint32_t od_destination(const uint32_t* __restrict__ row, int D, uint32_t u) {
-    int lo = 0, hi = D;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (u < __ldg(row + mid)) hi = mid; else lo = mid + 1;
+    if (u >= __ldg(row + D - 1)) return 0u;
+    int lo = 0, len = D;                    // invariant: the answer is in [lo, lo + len) and row[lo + len - 1] > u
+    while (len > 8) {
+        const int S = (len + 7) >> 3;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 1; i <= 7; ++i) {
+            const int idx = min(lo + i * S - 1, lo + len - 1);
+            cnt += u >= __ldg(row + idx) ? 1 : 0;       // pivots <= u form a prefix; a clamped pivot is > u
+        }
+        lo += cnt * S;
+        len = min(S, len - cnt * S);
     }
-    return lo < D ? (uint32_t)lo : 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < len) cnt += u >= __ldg(row + lo + i) ? 1 : 0;
+    return (uint32_t)(lo + cnt);
 }
 
-// ------------------------------------------------------------------------------------------------ main kernel
+// ------------------------------------------------------------------------------------------------ sweep + event kernels
+// One sub-step is three launches:
+//   abm_sweep_kernel    every agent slot, one warp per sub-tile: the DENSE work -- household hazards, the infection draw
+//                       I(k-1), detection of due transitions, the movement of everybody who simply goes to work / goes
+//                       home, and the pressure / head-count accumulation A(k).  It never touches a cold vector and has
+//                       no rare code path: an agent that needs one -- newly infected, a scheduled event due, away on a
+//                       trip at a movement hour, leaving the district -- is DEFERRED: its slot is appended to an event
+//                       queue and the sweep leaves it alone (no movement, no accumulation, words written back as read).
+//   abm_event_kernel    one THREAD per deferred agent (full warps instead of the 1-3 active lanes these bodies had inside
+//                       the sweep): infection event, due transitions, its movement, its table contribution -- the
+//                       reference's order of operations for that one agent -- and the store of its hot words.
+//   abm_hazard_table_kernel   tables -> thresholds, day log, clock (unchanged).
+// All table sums are integers, every draw is keyed by (agent, sub-step, site), so splitting the agents between the two
+// kernels cannot change a result.
 constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
+constexpr int EVENT_THREADS = 128;        // x 16 CTAs per SM at 32 registers: every queue of a busy night sub-step in ONE wave
 
-// Funnel loops: iterate a body over the agents whose bit is set in the per-lane `mask`.  Inside, J is
-// the agent's index 0..3 within the lane and fj / aj are its flags / aux words (read-only in ABM_FUNNEL_RO,
-// written back with the dirty flags in ABM_FUNNEL_RW).
+// Funnel loop (rare, irregular locations only): iterate a body over the agents whose bit is set in the per-lane `mask`.
+// Inside, J is the agent's index 0..3 within the lane and fj / aj are its flags / aux words.
 #define ABM_FUNNEL_RO(mask, ...)                                                     \
     while (__any_sync(FULL, (mask) != 0u)) {                                         \
         if (mask) {                                                                  \
@@ -482,35 +550,42 @@ constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
             __VA_ARGS__                                                              \
         }                                                                            \
     }
-#define ABM_FUNNEL_RW(mask, ...)                                                     \
-    while (__any_sync(FULL, (mask) != 0u)) {                                         \
-        if (mask) {                                                                  \
-            const int J = __ffs(mask) - 1;                                           \
-            (mask) &= (mask) - 1u;                                                   \
-            uint32_t fj = J == 0 ? f0 : (J == 1 ? f1 : (J == 2 ? f2 : f3));          \
-            uint32_t aj = J == 0 ? a0 : (J == 1 ? a1 : (J == 2 ? a2 : a3));          \
-            __VA_ARGS__                                                              \
-            if (J == 0) { f0 = fj; a0 = aj; } else if (J == 1) { f1 = fj; a1 = aj; } \
-            else if (J == 2) { f2 = fj; a2 = aj; } else { f3 = fj; a3 = aj; }        \
-            dirty = true;                                                            \
-        }                                                                            \
+
+// Append the agents whose bit is set in `ev` (per-lane 4-bit mask; bit j = slot0 + j) to the event queue of this CTA's
+// queue group.  Entry = (slot | newly-infected << 31, flags, aux, 0): the hot words travel with the entry, so the event
+// kernel reads its queue coalesced and touches only the agent's cold sector.  One atomic per LANE that has anything to
+// append (few lanes do; the queues spread the atomics over up to 1024 addresses).
+#define ABM_PUSH_EVENTS(ev, newly)                                                                   \
+    if (ev) {                                                                                        \
+        const uint32_t q = blockIdx.x & Wk.q_mask;                                                   \
+        uint4* dst = Wk.q_entries + (size_t)q * Wk.q_cap + atomicAdd(Wk.q_count + q, (uint32_t)__popc(ev)); \
+        uint32_t m = (ev);                                                                           \
+        do {                                                                                         \
+            const uint32_t j = __ffs(m) - 1u;                                                        \
+            m &= m - 1u;                                                                             \
+            const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));    /* untouched */ \
+            const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                   \
+            *dst++ = make_uint4((slot0 + j) | ((((newly) >> j) & 1u) << 31), fj, aj, 0u);            \
+        } while (m);                                                                                 \
     }
 
 template <uint32_t MODE>
 __global__ void __launch_bounds__(THREADS)
-abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* __restrict__ clk, const uint32_t mode_rt) {
+abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* clk, const uint32_t mode_rt) {
     __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
     __shared__ unsigned int s_acc[WARPS][2 * ABM_MAX_STATUS];   // per-warp home-pool pressure sums / head counts
-    __shared__ int s_tally_all[WARPS][N_TALLY];       // per-warp event tallies: a warp shares nothing with its CTA
 
     const uint32_t mode_static = MODE == RUNTIME_MODE ? (mode_rt & 0xFFFFu) : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;
+    // The event kernel may be scheduled as soon as SM resources free up (i.e. while this grid drains): it waits for
+    // this grid's completion before it touches anything.
+    launch_dependents();
     const uint32_t sub = blockIdx.x * WARPS + wid;
     const unsigned long long info = __ldg(T.sub_info + sub);
-    const int L0 = (int)(info >> 48);                                        // home district of every agent here
-    const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;     // canonical id of this lane's first slot
+    const uint32_t L0 = (uint32_t)(info >> 48);                              // home district of every agent here
     const uint32_t slot0 = sub * SUB + lane * PER_LANE;
-    const int A = T.A;
+    const uint32_t A = (uint32_t)T.A;
 
     // streaming loads / stores (evict-first): the hot words are touched once per launch and must not push the small
     // tables every warp re-reads out of L1
@@ -520,186 +595,169 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
     // words so the household phase does not wait for a dependent DRAM round trip
     uint32_t ix = 0;
     if (mode_static & M_INFECT) ix = __ldcs(G.hh_index + (slot0 >> 2));
+    // movement classes (go-out only): requested now, used after the infection phase
+    uint2 mc = make_uint2(0u, 0u);
+    if (mode_static & M_GO_OUT) mc = __ldcs(reinterpret_cast<const uint2*>(G.move_class + slot0));
 
-    int* s_tally = s_tally_all[wid];
-    if (lane < N_TALLY) s_tally[lane] = 0;
-    if (lane < 2 * ABM_MAX_STATUS) s_acc[wid][lane] = 0u;
-    __syncwarp();
+    unsigned int* acc_w = s_acc[wid];
+    if ((mode_static & M_DENSE_A) && !(mode_static & M_INCR)) {
+        if (lane < 2 * ABM_MAX_STATUS) acc_w[lane] = 0u;
+        __syncwarp();
+    }
 
     uint32_t f0 = f4.x, f1 = f4.y, f2 = f4.z, f3 = f4.w;
     uint32_t a0 = a4.x, a1 = a4.y, a2 = a4.z, a3 = a4.w;
-    bool dirty = false;
     // return ticks of the travellers among the four agents (movement sub-steps only): requested now so the DRAM round
-    // trip overlaps the infection and transition phases instead of stalling the movement phase
+    // trip overlaps the infection phase instead of stalling the movement phase
     int32_t tr0 = T_NEVER, tr1 = T_NEVER, tr2 = T_NEVER, tr3 = T_NEVER;
     if (mode_static & (M_GO_OUT | M_GO_HOME)) {
-        if (f0 & F_AWAY) tr0 = __ldcs(G.t_return + slot0 + 0);
-        if (f1 & F_AWAY) tr1 = __ldcs(G.t_return + slot0 + 1);
-        if (f2 & F_AWAY) tr2 = __ldcs(G.t_return + slot0 + 2);
-        if (f3 & F_AWAY) tr3 = __ldcs(G.t_return + slot0 + 3);
+        if (f0 & F_AWAY) tr0 = __ldcs(G.cold + (size_t)(slot0 + 0u) * ABM_COLD_WORDS + ABM_COLD_T_RETURN);
+        if (f1 & F_AWAY) tr1 = __ldcs(G.cold + (size_t)(slot0 + 1u) * ABM_COLD_WORDS + ABM_COLD_T_RETURN);
+        if (f2 & F_AWAY) tr2 = __ldcs(G.cold + (size_t)(slot0 + 2u) * ABM_COLD_WORDS + ABM_COLD_T_RETURN);
+        if (f3 & F_AWAY) tr3 = __ldcs(G.cold + (size_t)(slot0 + 3u) * ABM_COLD_WORDS + ABM_COLD_T_RETURN);
     }
     uint32_t* hz = s_hz[wid];
-    unsigned int* acc_w = s_acc[wid];
 
     // ================================================================ I(k-1): infection draws
     uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;          // 31-bit infection thresholds of the four agents
     if (mode_static & M_INFECT) {
         // ---- household term: 1 - prod(1 - 3 r_i) over contagious members present (base_model.py:156-175, 184-187)
         constexpr uint32_t CH_MASK = F_EPI_MASK | LOCF | F_BIGHH, CH_VAL = EPI_C | (LOC_HOME << F_LOC_SHIFT);
+        constexpr uint32_t SH_VAL = EPI_S | (LOC_HOME << F_LOC_SHIFT);
         const bool c0 = (f0 & CH_MASK) == CH_VAL, c1 = (f1 & CH_MASK) == CH_VAL, c2 = (f2 & CH_MASK) == CH_VAL,
                    c3 = (f3 & CH_MASK) == CH_VAL;
-        if (__any_sync(FULL, c0 | c1 | c2 | c3)) {
+        const bool h0 = (f0 & CH_MASK) == SH_VAL, h1 = (f1 & CH_MASK) == SH_VAL, h2 = (f2 & CH_MASK) == SH_VAL,
+                   h3 = (f3 & CH_MASK) == SH_VAL;
+        // somebody contagious at home AND somebody susceptible at home in this sub-tile, else no household can infect
+        if (__any_sync(FULL, c0 | c1 | c2 | c3) && __any_sync(FULL, h0 | h1 | h2 | h3)) {
             const uint32_t i0 = ix & 0xFFu, i1 = (ix >> 8) & 0xFFu, i2 = (ix >> 16) & 0xFFu, i3 = ix >> 24;
-            const int n_hh = (int)((__shfl_sync(FULL, i3, 31) + 1u) & 0xFFu);   // 255 = headless run of a big household
+            const uint32_t n_hh = (__shfl_sync(FULL, i3, 31) + 1u) & 0xFFu;   // 255 = headless run of a big household
             *reinterpret_cast<uint4*>(hz + lane * 4) = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
-            const uint32_t* q = T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0);
-            if (c0) atomicAdd(hz + i0, __ldg(q + rate_index(f0)));
-            if (c1) atomicAdd(hz + i1, __ldg(q + rate_index(f1)));
-            if (c2) atomicAdd(hz + i2, __ldg(q + rate_index(f2)));
-            if (c3) atomicAdd(hz + i3, __ldg(q + rate_index(f3)));
+            const uint32_t qoff = T.hw_rows > 1 ? L0 * 256u : 0u;
+            if (c0) atomicAdd(hz + i0, __ldg(T.qfx + (qoff + rate_index(f0))));
+            if (c1) atomicAdd(hz + i1, __ldg(T.qfx + (qoff + rate_index(f1))));
+            if (c2) atomicAdd(hz + i2, __ldg(T.qfx + (qoff + rate_index(f2))));
+            if (c3) atomicAdd(hz + i3, __ldg(T.qfx + (qoff + rate_index(f3))));
             __syncwarp();
-            for (int h = lane; h < n_hh; h += 32)     // one threshold per household (0 when nobody is contagious)
-                hz[h] = hazard_threshold_q24(T.omexp, hz[h]);
+#pragma unroll 1
+            for (uint32_t h = lane; h < n_hh; h += 32) {     // one threshold per household with somebody contagious
+                const uint32_t hq = hz[h];
+                if (hq) hz[h] = hazard_threshold_q24(T.omexp, hq);
+            }
             __syncwarp();
-            constexpr uint32_t SH_VAL = EPI_S | (LOC_HOME << F_LOC_SHIFT);
-            if ((f0 & CH_MASK) == SH_VAL) t0 = hz[i0];
-            if ((f1 & CH_MASK) == SH_VAL) t1 = hz[i1];
-            if ((f2 & CH_MASK) == SH_VAL) t2 = hz[i2];
-            if ((f3 & CH_MASK) == SH_VAL) t3 = hz[i3];
+            if (h0) t0 = hz[i0];
+            if (h1) t1 = hz[i1];
+            if (h2) t2 = hz[i2];
+            if (h3) t3 = hz[i3];
         }
     }
 
-    // Everything above depends only on the agent store, which the previous sub-step kernel finished writing
+    // Everything above depends only on the agent store, which the previous event kernel finished writing
     // before the table kernel started.  From here on the outputs of the table kernel are needed: thresholds,
     // cleared accumulators, the advanced clock.
     grid_dependency_wait();
-    // The table kernel may become resident now; it waits for this grid before it reads what the grid writes.  (Only
-    // after the wait above: everything the table kernel reads early was written by its predecessor, which every CTA
-    // of this grid has now seen complete.)
-    if (!(mode_rt & M_NO_EARLY_DEPENDENTS)) launch_dependents();
     const StepArgs s = step_args(T, clk, mode_static);
     const uint32_t mode = s.mode;
-    unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
 
+    uint32_t newly = 0;
     if (mode & M_INFECT) {
         // ---- outside pools and big households: susceptible and not (at home in a small household).
         // Home-district pool and trip destinations are one table look-up (predicated, all four agents);
         // schools, the hospital of district 0 and big households are rare and go through the funnel.
-        {
-            constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT;
-            uint32_t odd = 0;
-            if (mode & M_DENSE_I) {
-                // daytime: almost everybody is in the outside pool of the home district -> row in registers
-                const uint32_t row_thr = lane < A ? __ldg(Wk.thr_out + L0 * A + lane) : 0u;
-                const uint32_t r0 = __shfl_sync(FULL, row_thr, status_of(f0)), r1 = __shfl_sync(FULL, row_thr, status_of(f1));
-                const uint32_t r2 = __shfl_sync(FULL, row_thr, status_of(f2)), r3 = __shfl_sync(FULL, row_thr, status_of(f3));
+        constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT;
+        uint32_t odd = 0;
+        if (mode & M_DENSE_I) {
+            // daytime: almost everybody is in the outside pool of the home district -> row in registers
+            const uint32_t row_thr = lane < (int)A ? ld_ca(Wk.thr_out + L0 * A + lane) : 0u;
+            const uint32_t r0 = __shfl_sync(FULL, row_thr, status_of(f0)), r1 = __shfl_sync(FULL, row_thr, status_of(f1));
+            const uint32_t r2 = __shfl_sync(FULL, row_thr, status_of(f2)), r3 = __shfl_sync(FULL, row_thr, status_of(f3));
 #define ABM_OUT_THR(fj, aj, rj, tj, bit)                                                             \
-                if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
-                    const uint32_t lf = (fj) & LOCF;                                                 \
-                    if (lf == IN_HOMEPOOL) tj = rj;                                                  \
-                    else if (lf == IN_DEST) tj = __ldg(Wk.thr_out + cur_of(aj) * A + status_of(fj)); \
-                    else odd |= (bit);                                                               \
-                }
-                ABM_OUT_THR(f0, a0, r0, t0, 1u)
-                ABM_OUT_THR(f1, a1, r1, t1, 2u)
-                ABM_OUT_THR(f2, a2, r2, t2, 4u)
-                ABM_OUT_THR(f3, a3, r3, t3, 8u)
-#undef ABM_OUT_THR
-            } else {
-                // night: only travellers and the few agents of quirk Q4 are in an outside pool.  Straight-line,
-                // predicated look-ups (the four loads are in flight together; no divergent loop to resolve).
-#define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
-                if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {               \
-                    const uint32_t lf = (fj) & LOCF;                                                 \
-                    if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL))                               \
-                        tj = __ldg(Wk.thr_out + (lf == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj)); \
-                    else odd |= (bit);                                                               \
-                }
-                ABM_OUT_THR(f0, a0, t0, 1u)
-                ABM_OUT_THR(f1, a1, t1, 2u)
-                ABM_OUT_THR(f2, a2, t2, 4u)
-                ABM_OUT_THR(f3, a3, t3, 8u)
-#undef ABM_OUT_THR
+            if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {                   \
+                const uint32_t lf = (fj) & LOCF;                                                     \
+                if (lf == IN_HOMEPOOL) tj = rj;                                                      \
+                else if (lf == IN_DEST) tj = ld_ca(Wk.thr_out + (cur_of(aj) * A + status_of(fj)));  \
+                else odd |= (bit);                                                                   \
             }
-            ABM_FUNNEL_RO(odd, {
-                uint32_t thr = 0;
-                if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
-                    thr = hazard_threshold_fx(T.omexp, ((s.k & 1) ? Wk.hbig2[0] : Wk.hbig2[1])[big_slot(T, cid0 + J)] << 8);
-                } else {
-                    const int pool = pool_of(G, fj, aj, slot0 + J, L0);
-                    if (pool >= 0) thr = __ldg(Wk.thr_out + pool * A + status_of(fj));
-                }
-                if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
-            })
+            ABM_OUT_THR(f0, a0, r0, t0, 1u)
+            ABM_OUT_THR(f1, a1, r1, t1, 2u)
+            ABM_OUT_THR(f2, a2, r2, t2, 4u)
+            ABM_OUT_THR(f3, a3, r3, t3, 8u)
+#undef ABM_OUT_THR
+        } else {
+            // night: only travellers and the few agents of quirk Q4 are in an outside pool.  Straight-line,
+            // predicated look-ups (the four loads are in flight together; no divergent loop to resolve).
+#define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
+            if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {                   \
+                const uint32_t lf = (fj) & LOCF;                                                     \
+                if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL))                                   \
+                    tj = ld_ca(Wk.thr_out + ((lf == IN_DEST ? cur_of(aj) : L0) * A + status_of(fj))); \
+                else odd |= (bit);                                                                   \
+            }
+            ABM_OUT_THR(f0, a0, t0, 1u)
+            ABM_OUT_THR(f1, a1, t1, 2u)
+            ABM_OUT_THR(f2, a2, t2, 4u)
+            ABM_OUT_THR(f3, a3, t3, 8u)
+#undef ABM_OUT_THR
         }
+        ABM_FUNNEL_RO(odd, {
+            uint32_t thr = 0;
+            if (loc_of(fj) == LOC_HOME) {        // big household: hazard accumulated by the previous launch
+                const int64_t cid = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE + J;
+                thr = hazard_threshold_fx(T.omexp, __ldcg(((s.k & 1) ? Wk.hbig2[0] : Wk.hbig2[1]) + big_slot(T, cid)) << 8);
+            } else {
+                const int pool = pool_of(G, fj, aj, slot0 + J, (int)L0);
+                if (pool >= 0) thr = ld_ca(Wk.thr_out + ((uint32_t)pool * A + status_of(fj)));
+            }
+            if (J == 0) t0 = thr; else if (J == 1) t1 = thr; else if (J == 2) t2 = thr; else t3 = thr;
+        })
         // ---- the draw: one Philox block for the four agents of the lane
-        uint32_t newly = 0;
         if (t0 | t1 | t2 | t3) {
+            const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;
             const U4 X = group_draws(T, cid0, s.k_inf, SITE_INFECT);
             newly = ((X.x >> 1) < t0 ? 1u : 0u) | ((X.y >> 1) < t1 ? 2u : 0u) | ((X.z >> 1) < t2 ? 4u : 0u) |
                     ((X.w >> 1) < t3 ? 8u : 0u);
         }
-        // ---- disease course of the newly infected
-        ABM_FUNNEL_RW(newly, {
-            fj = infect_agent(T, G, fj, aj, slot0 + J, cid0 + J, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
-            atomicAdd(s_tally + CUM_INFECTED, 1);
-        })
     }
 
+    uint32_t defer = newly;           // agents handed to the event kernel
     if (mode & M_STEP) {
-        // ============================================================ T(k): due transitions
+        // ============================================================ T(k): due transitions -> event kernel
         {
             const uint32_t lim = ((uint32_t)s.k << 16) | 0xFFFFu;      // fire index (high half of aux) <= k
-            uint32_t due = (a0 <= lim ? 1u : 0u) | (a1 <= lim ? 2u : 0u) | (a2 <= lim ? 4u : 0u) | (a3 <= lim ? 8u : 0u);
-            if (mode & M_INCR) {
-                DeltaSink sink;
-                sink.acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
-                sink.acc_n = sink.acc_r + (size_t)T.P * A;
-                sink.hbig = (s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
-                sink.L0 = L0;
-                ABM_FUNNEL_RW(due, { sink.cid = cid0 + J; fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally, &sink); })
-            } else {
-                ABM_FUNNEL_RW(due, { fj = transition_agent(T, G, fj, aj, slot0 + J, s.now, s_tally); })
-            }
+            defer |= (a0 <= lim ? 1u : 0u) | (a1 <= lim ? 2u : 0u) | (a2 <= lim ? 4u : 0u) | (a3 <= lim ? 8u : 0u);
         }
+        bool dirty = false, adirty = false;
 
         // ============================================================ M(k): movement (base_model.py:274-441)
         if (mode & M_GO_HOME) {                                                         // :274-302
-            uint32_t away = 0;
-#define ABM_GO_HOME(fj, bit)                                                                         \
-            if (is_active(fj)) {                                                                     \
-                if ((fj) & F_AWAY) away |= (bit);                                                    \
-                else if ((fj) & LOCF) { fj &= ~LOCF; dirty = true; }            /* LOC_HOME == 0 */  \
+#define ABM_GO_HOME(fj, aj, trj, bit)                                                                \
+            if (!(defer & (bit)) && is_active(fj)) {                                                 \
+                if ((fj) & F_AWAY) {                                                                 \
+                    if ((trj) < s.now) {                                                /* :285-293 */  \
+                        aj = ((aj) & 0xFFFF0000u) | L0;                                              \
+                        fj = (fj) & ~(F_AWAY | LOCF);                                                \
+                        dirty = true; adirty = true;                                                 \
+                    }                                                                                \
+                } else if ((fj) & LOCF) { fj &= ~LOCF; dirty = true; }          /* LOC_HOME == 0 */  \
             }
-            ABM_GO_HOME(f0, 1u)
-            ABM_GO_HOME(f1, 2u)
-            ABM_GO_HOME(f2, 4u)
-            ABM_GO_HOME(f3, 8u)
+            ABM_GO_HOME(f0, a0, tr0, 1u)
+            ABM_GO_HOME(f1, a1, tr1, 2u)
+            ABM_GO_HOME(f2, a2, tr2, 4u)
+            ABM_GO_HOME(f3, a3, tr3, 8u)
 #undef ABM_GO_HOME
-#define ABM_BACK_HOME(fj, aj, trj, bit)                                                              \
-            if ((away & (bit)) && (trj) < s.now) {                                      /* :285-293 */  \
-                aj = ((aj) & 0xFFFF0000u) | (uint32_t)L0;                                            \
-                fj = (fj) & ~(F_AWAY | LOCF);                                                        \
-                dirty = true;                                                                        \
-            }
-            ABM_BACK_HOME(f0, a0, tr0, 1u)
-            ABM_BACK_HOME(f1, a1, tr1, 2u)
-            ABM_BACK_HOME(f2, a2, tr2, 4u)
-            ABM_BACK_HOME(f3, a3, tr3, 8u)
-#undef ABM_BACK_HOME
         }
         if (mode & M_GO_OUT) {                                                          // :304-340
-            const uint2 mc = __ldcs(reinterpret_cast<const uint2*>(G.move_class + slot0));
-            const uint32_t* thr_col = T.move_thr + ((mode & M_WEEKDAY) ? 0 : 2);
-            const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
-            const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
+            const uint32_t thr_col = (mode & M_WEEKDAY) ? 0u : 2u;
+            const uint32_t od_base = ((uint32_t)s.weekday * (uint32_t)T.D + L0) * (uint32_t)T.D + L0;
+            const uint32_t od_lo = L0 > 0 ? __ldg(T.od_thr + (od_base - 1u)) : 0u, od_hi = __ldg(T.od_thr + od_base);
+            const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;
             const U4 XM = group_draws(T, cid0, s.k, SITE_MOVER);
             uint32_t mover = 0, want_od = 0;
 #define ABM_MOVER(fj, cls, xm, bit)                                                                  \
-            if (is_active(fj)) {                                                                     \
+            if (!(defer & (bit)) && is_active(fj)) {                                                 \
                 const bool mild = T.mild_active && ((fj) & F_ONSET) && ((fj) & F_EPI_MASK) < EPI_R;   /* :212-219, :316 */ \
-                const uint32_t thr = __ldg(thr_col + 4u * (cls) + (mild ? 1 : 0));                    \
+                const uint32_t thr = __ldg(T.move_thr + (thr_col + 4u * (cls) + (mild ? 1u : 0u)));   \
                 if (((xm) >> 1) < thr) {                                                /* :317-318 a mover */ \
                     mover |= (bit);                                                                  \
                     if ((fj) & F_DMOVER) want_od |= (bit);                                           \
@@ -710,166 +768,286 @@ abm_substep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const
             ABM_MOVER(f2, mc.y & 0xFFFFu, XM.z, 4u)
             ABM_MOVER(f3, mc.y >> 16, XM.w, 8u)
 #undef ABM_MOVER
-            // district movers at home whose OD draw falls in the stay-home interval of their row, and movers
-            // that are neither away nor district movers, just go about their economic activity
-            uint32_t away = 0, leave = 0;   // movers that are away on paper / whose draw leaves the home district
+            // District movers whose OD draw falls outside the stay-home interval of their row leave the district: the
+            // destination search and the length of stay are the event kernel's.  Travellers are back in the home district
+            // when the stay is over (:342-360), then like everybody else.  All other movers go about their economic activity.
             U4 XO = U4{0u, 0u, 0u, 0u};
             if (want_od) XO = group_draws(T, cid0, s.k, SITE_OD);
-#define ABM_GO_OUT(fj, xo, bit)                                                                      \
+#define ABM_GO_OUT(fj, aj, trj, xo, bit)                                                             \
             if (mover & (bit)) {                                                                     \
                 const uint32_t u = (xo) >> 1;                                                        \
-                if ((fj) & F_AWAY) away |= (bit);                                                    \
-                else if (((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi)) leave |= (bit);            \
-                else { const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf; } \
-            }
-            ABM_GO_OUT(f0, XO.x, 1u)
-            ABM_GO_OUT(f1, XO.y, 2u)
-            ABM_GO_OUT(f2, XO.z, 4u)
-            ABM_GO_OUT(f3, XO.w, 8u)
-#undef ABM_GO_OUT
-            // travellers: back in the home district when the stay is over (:342-360), then like everybody else
-#define ABM_TRAVELLER(fj, aj, trj, xo, bit)                                                          \
-            if (away & (bit)) {                                                                      \
-                bool out_again = false;                                                              \
-                if ((trj) < s.now) {                                                                 \
-                    aj = ((aj) & 0xFFFF0000u) | (uint32_t)L0;                                        \
-                    fj &= ~F_AWAY;                                                                   \
-                    const uint32_t u = (xo) >> 1;                                                    \
-                    out_again = ((fj) & F_DMOVER) && !(u >= od_lo && u < od_hi);                     \
+                const bool leaves = (want_od & (bit)) && !(u >= od_lo && u < od_hi);                 \
+                if (((fj) & F_AWAY) && !((trj) < s.now)) {                                           \
+                    /* away on paper, not due back: economic activity of the HOME district (quirk Q4) */ \
+                    const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf;     \
+                } else if (leaves) defer |= (bit);       /* incl. a traveller who is due back and leaves again */ \
+                else {                                                                               \
+                    if ((fj) & F_AWAY) { aj = ((aj) & 0xFFFF0000u) | L0; fj &= ~F_AWAY; dirty = true; adirty = true; } \
+                    const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf;     \
                 }                                                                                    \
-                if (out_again) leave |= (bit);                                                       \
-                else fj = set_loc(fj, econ_loc(fj));                                    /* :331-339, :346-352 */ \
-                dirty = true;                                                                        \
             }
-            ABM_TRAVELLER(f0, a0, tr0, XO.x, 1u)
-            ABM_TRAVELLER(f1, a1, tr1, XO.y, 2u)
-            ABM_TRAVELLER(f2, a2, tr2, XO.z, 4u)
-            ABM_TRAVELLER(f3, a3, tr3, XO.w, 8u)
-#undef ABM_TRAVELLER
-            // district movers whose draw is not in the stay-home interval: find the destination (:366-441)
-            ABM_FUNNEL_RW(leave, {
-                const uint32_t dest = od_destination(od_row, T.D, word_of(XO, J) >> 1);
-                if (dest != (uint32_t)L0) {                                             // :410-439
-                    const U4 XS = group_draws(T, cid0, s.k, SITE_STAY);
-                    G.t_return[slot0 + J] = stay_return_tick(T, word_of(XS, J), s.weekday, (uint32_t)L0, dest, s.now);
-                    fj = set_loc(fj, LOC_DEST) | F_AWAY;
-                    aj = (aj & 0xFFFF0000u) | dest;
-                } else {
-                    fj = set_loc(fj, econ_loc(fj));
-                }
-            })
+            ABM_GO_OUT(f0, a0, tr0, XO.x, 1u)
+            ABM_GO_OUT(f1, a1, tr1, XO.y, 2u)
+            ABM_GO_OUT(f2, a2, tr2, XO.z, 4u)
+            ABM_GO_OUT(f3, a3, tr3, XO.w, 8u)
+#undef ABM_GO_OUT
         }
 
         // ============================================================ A(k): pressure / headcount tables
         if (!(mode & M_INCR)) {
-        unsigned long long* acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
-        unsigned long long* acc_n = acc_r + (size_t)T.P * A;
-        // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
-        // destinations: predicated global adds.  Schools, the hospital of district 0 (quirk Q3) and
-        // contagious members of big households at home are rare and go through the funnel.
-        constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT, IN_POOL = LOC_POOL << F_LOC_SHIFT, IN_HOSP = LOC_HOSP << F_LOC_SHIFT;
-        constexpr uint32_t BH_MASK = F_EPI_MASK | LOCF | F_BIGHH, BH_VAL = EPI_C | F_BIGHH;
-        uint32_t work = 0;
-        if (mode & M_DENSE_A) {
-            // per-lane head counts in 4-bit fields (status 0..11), widened to bytes for three warp reductions
-            unsigned long long cw = 0ull;
-            uint32_t dest = 0;
+            unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
+            unsigned long long* acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+            unsigned long long* acc_n = acc_r + (size_t)T.P * A;
+            // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
+            // destinations: predicated global adds.  Schools, the hospital of district 0 (quirk Q3) and
+            // contagious members of big households at home are rare and go through the funnel.  Deferred agents
+            // are counted by the event kernel, after their events.
+            constexpr uint32_t IN_DEST = LOC_DEST << F_LOC_SHIFT, IN_POOL = LOC_POOL << F_LOC_SHIFT, IN_HOSP = LOC_HOSP << F_LOC_SHIFT;
+            constexpr uint32_t BH_MASK = F_EPI_MASK | LOCF | F_BIGHH, BH_VAL = EPI_C | F_BIGHH;
+            uint32_t work = 0;
+            if (mode & M_DENSE_A) {
+                // per-lane head counts in 4-bit fields (status 0..11), widened to bytes for three warp reductions
+                unsigned long long cw = 0ull;
+                uint32_t dest = 0;
 #define ABM_COUNT(fj, bit)                                                                           \
-            {                                                                                        \
-                const uint32_t lf = (fj) & LOCF;                                                     \
-                if (lf == IN_HOMEPOOL) {                                                             \
-                    cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);                          \
-                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj))); \
-                } else if (lf == IN_DEST) dest |= (bit);                                             \
-                else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
-            }
-            ABM_COUNT(f0, 1u)
-            ABM_COUNT(f1, 2u)
-            ABM_COUNT(f2, 4u)
-            ABM_COUNT(f3, 8u)
+                if (!(defer & (bit))) {                                                              \
+                    const uint32_t lf = (fj) & LOCF;                                                 \
+                    if (lf == IN_HOMEPOOL) {                                                         \
+                        cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);                      \
+                        if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj))); \
+                    } else if (lf == IN_DEST) dest |= (bit);                                         \
+                    else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                }
+                ABM_COUNT(f0, 1u)
+                ABM_COUNT(f1, 2u)
+                ABM_COUNT(f2, 4u)
+                ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
 #define ABM_ADD_DEST(fj, aj, bit)                                                                    \
-            if (dest & (bit)) {                                                                      \
-                const uint32_t e = cur_of(aj) * A + status_of(fj);                                   \
-                atomicAdd(acc_n + e, 1ull);                                                          \
-                if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
-            }
-            ABM_ADD_DEST(f0, a0, 1u)
-            ABM_ADD_DEST(f1, a1, 2u)
-            ABM_ADD_DEST(f2, a2, 4u)
-            ABM_ADD_DEST(f3, a3, 8u)
+                if (dest & (bit)) {                                                                  \
+                    const uint32_t e = cur_of(aj) * A + status_of(fj);                               \
+                    atomicAdd(acc_n + e, 1ull);                                                      \
+                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+                }
+                ABM_ADD_DEST(f0, a0, 1u)
+                ABM_ADD_DEST(f1, a1, 2u)
+                ABM_ADD_DEST(f2, a2, 4u)
+                ABM_ADD_DEST(f3, a3, 8u)
 #undef ABM_ADD_DEST
-            const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
-            const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
-            const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
-            const uint32_t hi = __reduce_add_sync(FULL, (hi32 & 0x0F0Fu) | (((hi32 >> 4) & 0x0F0Fu) << 16));   // 8,10 | 9,11
-            if (lane < A) {
-                const uint32_t w = lane < 8 ? ((lane & 1) ? od : ev) : hi;
-                const uint32_t sh = lane < 8 ? 8u * (lane >> 1) : 8u * (((lane - 8) >> 1) + 2 * ((lane - 8) & 1));
-                acc_w[ABM_MAX_STATUS + lane] += (w >> sh) & 0xFFu;       // this warp's own accumulator row
-            }
-        } else {
-            // night: hardly anybody is in an outside pool
-            uint32_t pooled = 0;
+                const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
+                const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
+                const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
+                const uint32_t hi = __reduce_add_sync(FULL, (hi32 & 0x0F0Fu) | (((hi32 >> 4) & 0x0F0Fu) << 16));   // 8,10 | 9,11
+                if (lane < (int)A) {
+                    const uint32_t w = lane < 8 ? ((lane & 1) ? od : ev) : hi;
+                    const uint32_t sh = lane < 8 ? 8u * (lane >> 1) : 8u * (((lane - 8) >> 1) + 2 * ((lane - 8) & 1));
+                    acc_w[ABM_MAX_STATUS + lane] += (w >> sh) & 0xFFu;       // this warp's own accumulator row
+                }
+            } else {
+                // night: hardly anybody is in an outside pool
+                uint32_t pooled = 0;
 #define ABM_COUNT(fj, bit)                                                                           \
-            {                                                                                        \
-                const uint32_t lf = (fj) & LOCF;                                                     \
-                if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) pooled |= (bit);                   \
-                else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
-            }
-            ABM_COUNT(f0, 1u)
-            ABM_COUNT(f1, 2u)
-            ABM_COUNT(f2, 4u)
-            ABM_COUNT(f3, 8u)
+                if (!(defer & (bit))) {                                                              \
+                    const uint32_t lf = (fj) & LOCF;                                                 \
+                    if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) pooled |= (bit);               \
+                    else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                }
+                ABM_COUNT(f0, 1u)
+                ABM_COUNT(f1, 2u)
+                ABM_COUNT(f2, 4u)
+                ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
 #define ABM_ADD_POOLED(fj, aj, bit)                                                                  \
-            if (pooled & (bit)) {                                                                    \
-                const uint32_t e = (((fj) & LOCF) == IN_DEST ? cur_of(aj) : (uint32_t)L0) * A + status_of(fj); \
-                atomicAdd(acc_n + e, 1ull);                                                          \
-                if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
-            }
-            ABM_ADD_POOLED(f0, a0, 1u)
-            ABM_ADD_POOLED(f1, a1, 2u)
-            ABM_ADD_POOLED(f2, a2, 4u)
-            ABM_ADD_POOLED(f3, a3, 8u)
+                if (pooled & (bit)) {                                                                \
+                    const uint32_t e = (((fj) & LOCF) == IN_DEST ? cur_of(aj) : L0) * A + status_of(fj); \
+                    atomicAdd(acc_n + e, 1ull);                                                      \
+                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
+                }
+                ABM_ADD_POOLED(f0, a0, 1u)
+                ABM_ADD_POOLED(f1, a1, 2u)
+                ABM_ADD_POOLED(f2, a2, 4u)
+                ABM_ADD_POOLED(f3, a3, 8u)
 #undef ABM_ADD_POOLED
-        }
-        ABM_FUNNEL_RO(work, {
-            const int pool = pool_of(G, fj, aj, slot0 + J, L0);
-            const bool cont = (fj & F_EPI_MASK) == EPI_C;
-            if (pool >= 0) {
-                const uint32_t e = (uint32_t)pool * A + status_of(fj);
-                atomicAdd(acc_n + e, 1ull);
-                if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
-            } else if (cont && (fj & (LOCF | F_BIGHH)) == F_BIGHH) {
-                const uint32_t qv = __ldg(T.qfx + (T.hw_rows > 1 ? (size_t)L0 * 256 : 0) + rate_index(fj));
-                atomicAdd(((s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0]) + big_slot(T, cid0 + J), (unsigned long long)qv);
             }
-        })
+            ABM_FUNNEL_RO(work, {
+                const int pool = pool_of(G, fj, aj, slot0 + J, (int)L0);
+                const bool cont = (fj & F_EPI_MASK) == EPI_C;
+                if (pool >= 0) {
+                    const uint32_t e = (uint32_t)pool * A + status_of(fj);
+                    atomicAdd(acc_n + e, 1ull);
+                    if (cont) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj)));
+                } else if (cont && (fj & (LOCF | F_BIGHH)) == F_BIGHH) {
+                    const int64_t cid = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE + J;
+                    const uint32_t qv = __ldg(T.qfx + ((T.hw_rows > 1 ? L0 * 256u : 0u) + rate_index(fj)));
+                    atomicAdd(((s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0]) + big_slot(T, cid), (unsigned long long)qv);
+                }
+            })
         }   // full recount
+
+        // ============================================================ write back what changed
+        // (aux changes only when a traveller returned; deferred agents keep the words they were read with)
+        if (dirty) {
+            __stcs(reinterpret_cast<uint4*>(G.flags + slot0), make_uint4(f0, f1, f2, f3));
+            if (mode & (M_GO_OUT | M_GO_HOME))
+                if (adirty) __stcs(reinterpret_cast<uint4*>(G.aux + slot0), make_uint4(a0, a1, a2, a3));
+        }
     }
 
-    // ================================================================ write back what changed
-    if (dirty) {
-        __stcs(reinterpret_cast<uint4*>(G.flags + slot0), make_uint4(f0, f1, f2, f3));
-        __stcs(reinterpret_cast<uint4*>(G.aux + slot0), make_uint4(a0, a1, a2, a3));
-    }
+    // ================================================================ hand the deferred agents to the event kernel
+    ABM_PUSH_EVENTS(defer, newly)
+    trace_stamp(Wk, s.k, 0, t_start);
 
-    // ================================================================ flush of the warp's counters
-    __syncwarp();
-    const uint32_t rep = blockIdx.x * WARPS + wid;     // replica of the accumulators this warp adds to
-    if (lane < N_TALLY) {
-        const int v = s_tally[lane];
-        if (v) atomicAdd(Wk.tally + (size_t)(rep & Wk.rep_mask) * N_TALLY + lane, (unsigned long long)(long long)v);
+    // ================================================================ flush of the warp's home-pool accumulators
+    if ((mode & M_DENSE_A) && !(mode & M_INCR)) {
+        __syncwarp();
+        if (lane < 2 * ABM_MAX_STATUS) {
+            // lanes 0..11: pressure sums, lanes 12..23: head counts of the warp's home district
+            const uint32_t b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
+            const unsigned int v = acc_w[lane];
+            if (v && b < A) {
+                unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
+                atomicAdd(acc_k + (size_t)(sub & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A) + (size_t)L0 * A + b,
+                          (unsigned long long)v);
+            }
+        }
     }
-    if ((mode & M_DENSE_A) && !(mode & M_INCR) && lane < 2 * ABM_MAX_STATUS) {
-        // lanes 0..11: pressure sums, lanes 12..23: head counts of the warp's home district
-        const int b = lane < ABM_MAX_STATUS ? lane : lane - ABM_MAX_STATUS;
-        const unsigned int v = acc_w[lane];
-        if (v && b < A)
-            atomicAdd(acc_k + (size_t)(rep & Wk.rep_mask) * (2u * T.P * A) + (lane < ABM_MAX_STATUS ? 0 : (size_t)T.P * A) + (size_t)L0 * A + b,
-                      (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------------------ event kernel
+// One thread per deferred agent.  What happens to it, in the reference's order for one agent: infection event of the
+// previous sub-step's draw (Country.set_epidemic_status, base_model.py:838-1055), due transitions
+// (update_agent_states + contagious promotion, :226-272, :54-58), go_home / go_out incl. the return from and the
+// departure on a trip (:274-441), and its contribution to the district x status tables.  The hot words come with the
+// queue entry (coalesced); the only scattered accesses are the agent's 32-byte cold sector and the final stores.
+__global__ void __launch_bounds__(EVENT_THREADS, 2048 / EVENT_THREADS)
+abm_event_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* clk, const uint32_t mode_rt) {
+    __shared__ int s_tally[N_TALLY];
+    const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;
+    if (threadIdx.x < N_TALLY) s_tally[threadIdx.x] = 0;
+    grid_dependency_wait();       // the sweep has completed: queue and agent store are visible
+    // first entry of this thread, requested together with the count and the clock (one round trip instead of three);
+    // beyond the count it is stale data inside the queue's allocation and is not used
+    uint4 e_first = __ldcs(Wk.q_entries + (size_t)blockIdx.x * Wk.q_cap + threadIdx.x);
+    // the table kernel may become resident (it waits for this grid before it reads what it writes); a flush is
+    // followed by a sweep, which reads the agent store in its prologue and must not start early
+    if (!(mode_rt & M_NO_EARLY_DEPENDENTS)) launch_dependents();
+    __syncthreads();
+    const StepArgs s = step_args(T, clk, mode_rt & 0xFFFFu);
+    const uint32_t mode = s.mode;
+    const uint32_t A = (uint32_t)T.A;
+
+    for (uint32_t q = blockIdx.x; q <= Wk.q_mask; q += gridDim.x) {
+        const uint32_t n = ld_ca(Wk.q_count + q);
+        const uint4* entries = Wk.q_entries + (size_t)q * Wk.q_cap;
+        for (uint32_t i = threadIdx.x; i < n; i += EVENT_THREADS) {
+            const uint4 e = (q == blockIdx.x && i == threadIdx.x) ? e_first : __ldcs(entries + i);
+            const uint32_t slot = e.x & 0x7FFFFFFFu;
+            uint32_t f = e.y, a = e.z;
+            Cold c = load_cold(G, slot);
+            const unsigned long long info = __ldg(T.sub_info + (slot >> 7));
+            const int L0 = (int)(info >> 48);
+            const int64_t cid = (int64_t)(info & 0xFFFFFFFFFFFFull) + (slot & (SUB - 1));
+            const int J = (int)(slot & 3u);                     // word of the group Philox blocks that is this agent's
+            bool cold_dirty = false;
+            if (e.x >> 31) {                                     // I(k-1): the draw infected this agent
+                f = infect_agent(T, f, a, c, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+                atomicAdd(s_tally + CUM_INFECTED, 1);
+                cold_dirty = true;
+            }
+            if (mode & M_STEP) {
+                if ((a >> 16) <= (uint32_t)s.k) {                // T(k)
+                    if (mode & M_INCR) {
+                        DeltaSink sink;
+                        sink.acc_r = ((s.k & 1) ? Wk.acc2[1] : Wk.acc2[0]) + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+                        sink.acc_n = sink.acc_r + (size_t)T.P * A;
+                        sink.hbig = (s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
+                        sink.L0 = L0; sink.cid = cid;
+                        f = transition_agent(T, G, f, a, slot, c, s.now, s_tally, &sink);
+                    } else {
+                        f = transition_agent(T, G, f, a, slot, c, s.now, s_tally);
+                    }
+                }
+                if ((mode & M_GO_HOME) && is_active(f)) {                               // base_model.py:274-302
+                    if (f & F_AWAY) {
+                        if (c.u.x < s.now) {                                            // :285-293
+                            a = (a & 0xFFFF0000u) | (uint32_t)L0;
+                            f &= ~(F_AWAY | LOCF);
+                        }
+                    } else {
+                        f &= ~LOCF;                                                     // LOC_HOME == 0
+                    }
+                }
+                if ((mode & M_GO_OUT) && is_active(f)) {                                // :304-340
+                    const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;     // :212-219, :316
+                    const uint32_t cls = G.move_class[slot];
+                    const uint32_t thr = __ldg(T.move_thr + (((mode & M_WEEKDAY) ? 0u : 2u) + 4u * cls + (mild ? 1u : 0u)));
+                    const uint32_t xm = word_of(group_draws(T, cid, s.k, SITE_MOVER), J);
+                    if ((xm >> 1) < thr) {                                              // :317-318 a mover
+                        const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
+                        uint32_t u = 0;
+                        bool leaves = false;
+                        if (f & F_DMOVER) {
+                            u = word_of(group_draws(T, cid, s.k, SITE_OD), J) >> 1;
+                            const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
+                            leaves = !(u >= od_lo && u < od_hi);
+                        }
+                        bool go = false;
+                        if (f & F_AWAY) {
+                            // travellers: back in the home district when the stay is over (:342-360), then like everybody else
+                            if (c.u.x < s.now) {
+                                a = (a & 0xFFFF0000u) | (uint32_t)L0;
+                                f &= ~F_AWAY;
+                                go = leaves;
+                            }
+                        } else {
+                            go = leaves;
+                        }
+                        bool econ = !go;
+                        if (go) {                                                       // :366-441
+                            const uint32_t dest = od_destination(od_row, T.D, u);
+                            if (dest != (uint32_t)L0) {                                 // :410-439
+                                const uint32_t xs = word_of(group_draws(T, cid, s.k, SITE_STAY), J);
+                                c.u.x = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
+                                cold_dirty = true;
+                                f = set_loc(f, LOC_DEST) | F_AWAY;
+                                a = (a & 0xFFFF0000u) | dest;
+                            } else {
+                                econ = true;
+                            }
+                        }
+                        if (econ) f = set_loc(f, econ_loc(f));                          // :331-339, :346-352
+                    }
+                }
+                if (!(mode & M_INCR)) {                                                 // A(k) of this one agent
+                    const Contribution cb = contribution_of(G, f, a, slot, L0);
+                    if (cb.pool >= 0) {
+                        unsigned long long* acc_r = ((s.k & 1) ? Wk.acc2[1] : Wk.acc2[0]) + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+                        const uint32_t en = (uint32_t)cb.pool * A + status_of(f);
+                        atomicAdd(acc_r + (size_t)T.P * A + en, 1ull);
+                        if (cb.cont) atomicAdd(acc_r + en, (unsigned long long)__ldg(T.rfx + rate_index(f)));
+                    } else if (cb.big_home) {
+                        const uint32_t qv = __ldg(T.qfx + ((T.hw_rows > 1 ? (uint32_t)L0 * 256u : 0u) + rate_index(f)));
+                        atomicAdd(((s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0]) + big_slot(T, cid), (unsigned long long)qv);
+                    }
+                }
+            }
+            G.flags[slot] = f;
+            G.aux[slot] = a;
+            if (cold_dirty) {
+                int4* p = reinterpret_cast<int4*>(G.cold) + (size_t)slot * 2;
+                p[0] = c.t;
+                p[1] = c.u;
+            }
+        }
+        __syncthreads();                  // every thread has read the count
+        if (threadIdx.x == 0) Wk.q_count[q] = 0u;
     }
+    __syncthreads();
+    if (threadIdx.x < N_TALLY) {
+        const int v = s_tally[threadIdx.x];
+        if (v) atomicAdd(Wk.tally + (size_t)(blockIdx.x & Wk.rep_mask) * N_TALLY + threadIdx.x, (unsigned long long)(long long)v);
+    }
+    trace_stamp(Wk, s.k, 1, t_start);
 }
 
 // ------------------------------------------------------------------------------------------------ table kernel
@@ -901,6 +1079,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
     __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
+    const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;
     // ---- before the dependency wait: everything that only this kernel's predecessor (the previous table kernel)
     // or the host wrote -- the clock, the kept sums, constants.  These loads overlap the tail of the sub-step kernel.
     const int k = clk->k;                               // the sub-step that is being executed by the primary grid
@@ -996,6 +1175,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
             Wk.thr_out[L * A + t] = thr;
         }
         __syncthreads();
+        trace_stamp(Wk, k, 2, t_start);
         if (t == 0 && ta.do_threshold) { __threadfence(); atomicAdd(Wk.rows_done, 1u); }
         return;
     }
@@ -1059,6 +1239,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
         clk->seeds_before = seeds_before + clk->seeds_at_now;
         clk->seeds_at_now = 0;
     }
+    trace_stamp(Wk, k, 2, t_start);
 }
 
 // ------------------------------------------------------------------------------------------------ seeding
@@ -1070,9 +1251,13 @@ __global__ void abm_seed_kernel(const DevTables T, const DevAgents G, unsigned l
     if (i < n) {
         const int64_t slot = slots[i];
         uint32_t a = G.aux[slot];
-        const uint32_t f = infect_agent(T, G, G.flags[slot], a, slot, ids[i], k, now, (uint32_t)k, tally);
+        Cold c = load_cold(G, (uint32_t)slot);
+        const uint32_t f = infect_agent(T, G.flags[slot], a, c, ids[i], k, now, (uint32_t)k, tally);
         G.flags[slot] = f;
         G.aux[slot] = a;
+        int4* p = reinterpret_cast<int4*>(G.cold) + (size_t)slot * 2;
+        p[0] = c.t;
+        p[1] = c.u;
     }
 }
 

@@ -33,6 +33,13 @@ extern "C" {
 #define ABM_LOG_STRIDE 16        /* int64 words per day-log row                                    */
 #define ABM_MAX_RANKS 16         /* ranks of one node that can share tables through peer memory    */
 #define ABM_IPC_HANDLE_BYTES 64  /* size of the opaque handle abm_peer_export produces             */
+#define ABM_COLD_WORDS 8         /* int32 words of an agent's cold (event-time) record              */
+#define ABM_COLD_T_INFECTED 0
+#define ABM_COLD_T_CONTAGIOUS 1
+#define ABM_COLD_T_ONSET 2
+#define ABM_COLD_T_RECOVERED 3
+#define ABM_COLD_T_RETURN 4
+#define ABM_COLD_INF_AT 5
 
 typedef enum {
     ABM_OK = 0,
@@ -118,12 +125,12 @@ typedef struct {
 typedef struct {
     uint32_t* flags;        /* [n_slots] packed state word                       */
     uint32_t* aux;          /* [n_slots] next-event sub-step << 16 | current district */
-    int32_t*  t_infected;   /* date_infected                                     */
-    int32_t*  t_contagious; /* date_start_contagious                             */
-    int32_t*  t_onset;      /* date_start_symptomatic                            */
-    int32_t*  t_recovered;  /* date_recovered                                    */
-    int32_t*  t_return;     /* return_district_at                                */
-    uint32_t* inf_at;       /* infected_at_{district,location}_ids               */
+    int32_t*  cold;         /* [n_slots][ABM_COLD_WORDS] event-time record, one 32-byte sector per agent,  */
+                            /* touched only when an event fires: word ABM_COLD_T_INFECTED date_infected,   */
+                            /* _T_CONTAGIOUS date_start_contagious, _T_ONSET date_start_symptomatic,       */
+                            /* _T_RECOVERED date_recovered, _T_RETURN return_district_at, _INF_AT          */
+                            /* infected_at_{district,location}_ids (kind << 16 | district); minute ticks,  */
+                            /* INT32_MAX = datetime.max; 32-byte aligned                                    */
     const uint16_t* move_class; /* movement-probability class                    */
     const uint32_t* econ_pool;  /* outside pool of EKIND_POOL agents, may be NULL */
     const uint8_t*  hh_index;   /* [n_slots] household index within the sub-tile  */
@@ -162,6 +169,13 @@ int abm_set_profiling(abm_handle* h, int32_t on);
 int abm_kernel_time(abm_handle* h, double* total_ms, int64_t* launches);
 /* Same bracket around the table kernel(s) (and the all-reduce) of every sub-step. */
 int abm_table_time(abm_handle* h, double* total_ms);
+/* Same bracket around the event kernel (the agents the sweep deferred: infections, due transitions, departures). */
+int abm_event_time(abm_handle* h, double* total_ms);
+/* Device-side timeline (measurement only): after abm_set_trace(h, n) every kernel of sub-steps 0..n-1 stamps the
+ * window [first CTA start, last CTA end] of its launch with the GPU's global nanosecond timer; abm_read_trace copies
+ * n rows of 6 uint64 (sweep start, end, event kernel start, end, table kernel start, end).  n = 0 switches it off. */
+int abm_set_trace(abm_handle* h, int32_t n_substeps);
+int abm_read_trace(abm_handle* h, uint64_t* out, int32_t n_substeps);
 /* Checkpoint / resume (the reference pickles the whole model, scenario_models.py:497-500): the agent
  * vectors are the caller's buffers; these two calls carry the rest -- the clock, the 12 running counters
  * and the number of seeded infections.  abm_get_state applies pending draws first (abm_flush). */

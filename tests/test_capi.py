@@ -12,13 +12,13 @@ def test_library_exports_all_declared_symbols(built_library):
     assert len(declared) >= 19
     for name in sorted(declared):
         assert hasattr(built_library, name), name
-    assert built_library.abm_version() == 100
+    assert built_library.abm_version() == 200
 
 
 def test_python_structs_match_header_layout(built_library):
     from abm_b200 import engine
     assert ct.sizeof(engine.AbmTables) == 16 * 8
-    assert ct.sizeof(engine.AbmAgentPtrs) == 11 * 8
+    assert ct.sizeof(engine.AbmAgentPtrs) == 6 * 8
     assert engine.AbmConfig.seed.offset % 8 == 0 and engine.AbmConfig.stream.offset % 8 == 0
 
 

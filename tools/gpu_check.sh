@@ -12,7 +12,7 @@ timeout 300 python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/plain
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none \
     -k regex:abm_ -s 480 -c 12 --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/ncu_$tag.log 2>&1
 if [ "$2" == "full" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:abm_substep -s 240 -c 6 -o gpurun_out/prof_$tag \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:abm_sweep -s 240 -c 6 -o gpurun_out/prof_$tag \
       python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/ncu2_$tag.log 2>&1
 fi
 cat gpurun_out/plain_$tag.log

@@ -23,7 +23,10 @@ for r in rows[hdr_idx[0] + 1:end]:
     except ValueError:
         continue
     text[line] = r[1]
-    s = float(r[col['# Samples']] or 0); n = float(r[col['Instructions Executed']] or 0)
+    try:
+        s = float(r[col['# Samples']] or 0); n = float(r[col['Instructions Executed']] or 0)
+    except ValueError:
+        continue
     samples[line] += s; insts[line] += n; tot_s += s; tot_i += n
     for c in stall_cols:
         v = r[col[c]]

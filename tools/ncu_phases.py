@@ -4,7 +4,7 @@
     python tools/ncu_phases.py src.csv [path/to/abm_kernels.cuh]
 
 Phases are found in the source itself: every `__device__` function and every `// ====... <title>` banner inside
-abm_substep_kernel starts one, so the ranges follow the code (the report must come from the same revision).
+abm_sweep_kernel starts one, so the ranges follow the code (the report must come from the same revision).
 """
 import csv
 import os
@@ -23,7 +23,7 @@ for no, line in enumerate(open(src), 1):
     if m:
         marks.append((no, 'fn ' + m.group(1)))
         in_kernel = False
-    if re.match(r'abm_substep_kernel\(', line):
+    if re.match(r'abm_sweep_kernel\(', line):
         marks.append((no, 'kernel prologue'))
         in_kernel = True
     b = re.match(r'\s*// =+ (.+)$', line)

@@ -58,7 +58,7 @@ us, rd, wr = col('gpu__time_duration.sum', 'us'), col('dram__bytes_read.sum', 'M
 n = len(us)
 json.dump({
     'bytes_per_launch': sum(a + b for a, b in zip(rd, wr)) * 1e6 / n,
-    'kernel': 'abm_substep_kernel',
+    'kernel': 'abm_sweep_kernel',
     'launches': n,
     'avg_ns_under_ncu': sum(us) * 1e3 / n,
     'source': f'profiles/r01_ncu_full_details_{tag}.csv (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, '

@@ -2,7 +2,7 @@
 
     python tools/sass_phases.py [MODE] [path/to/libabm_b200.so] [--lines N]
 
-MODE is the template argument of abm_substep_kernel (259 night, 135 go-out, 451 noon, 75 go-home, 1 flush; default
+MODE is the template argument of abm_sweep_kernel (259 night, 135 go-out, 451 noon, 75 go-home, 1 flush; default
 259).  The library must have been built with -lineinfo (the default build is).  Phases are the same as in
 tools/ncu_phases.py: every `__device__` function and every `// ====... <title>` banner of the kernel body.
 
@@ -30,7 +30,7 @@ def phase_marks(src):
         if m:
             marks.append((no, 'fn ' + m.group(1)))
             in_kernel = False
-        if re.match(r'abm_substep_kernel\(', line):
+        if re.match(r'abm_sweep_kernel\(', line):
             marks.append((no, 'kernel prologue'))
             in_kernel = True
         b = re.match(r'\s*// =+ (.+)$', line)
@@ -52,7 +52,7 @@ def main():
     cubin = sorted(f for f in os.listdir(tmp) if f.endswith('.cubin'))[0]
     text = subprocess.run([os.path.join(CUDA_BIN, 'nvdisasm'), '-g', '-c', os.path.join(tmp, cubin)], check=True,
                           capture_output=True, text=True).stdout
-    want = f'abm_substep_kernelILj{mode}E'
+    want = f'abm_sweep_kernelILj{mode}E'
     marks = phase_marks(SRC)
 
     def phase_of(line_no):
@@ -91,7 +91,7 @@ def main():
     total = sum(per_phase.values())
     if not total:
         sys.exit(f'no SASS found for {want} in {lib}')
-    print(f'abm_substep_kernel<{mode}>: {total} static SASS instructions')
+    print(f'abm_sweep_kernel<{mode}>: {total} static SASS instructions')
     for name, n in per_phase.most_common():
         print(f'  {name:44s} {n:6d}  {100 * n / total:5.1f}%')
     print('opcode mix:', ', '.join(f'{k} {v}' for k, v in ops.most_common(14)))
