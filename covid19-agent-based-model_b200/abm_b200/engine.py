@@ -418,9 +418,10 @@ class Simulation:
 
     def read_trace(self, n_substeps):
         """uint64 [n, 3 kernels (sweep, events, table), 2 (first CTA start, last CTA end)] in ns of the GPU timer."""
-        out = np.zeros((int(n_substeps), 3, 2), dtype=np.uint64)
+        out = np.zeros((int(n_substeps), 12), dtype=np.uint64)
         self._check(self.lib.abm_read_trace(self.h, _ptr(out), int(n_substeps)))
-        return out
+        self.trace_debug = out[:, 6:]
+        return np.ascontiguousarray(out[:, :6]).reshape(-1, 3, 2)
 
     def event_time(self):
         ms = ct.c_double()

@@ -165,6 +165,7 @@ DevWork make_work(const abm_handle* h) {
     w.max_log_rows = h->cfg.max_log_rows;
     w.rows_done = h->rows_done;
     w.trace = h->trace; w.trace_rows = h->trace_rows;
+    w.n_sub = (uint32_t)(h->cfg.n_tiles * (ABM_TILE / ABM_SUBTILE));
     w.q_entries = h->q_entries; w.q_count = h->q_count; w.q_mask = h->q_mask; w.q_cap = h->q_cap;
     w.n_ranks = 1; w.rank = 0;
     if (h->peers_attached) {
@@ -197,9 +198,11 @@ int launch_main(abm_handle* h, uint32_t mode) {
         if ((rc = timed_pair(h, h->prof_event_events, h->prof_event_used, &v0, &v1))) return rc;
         CUDA_TRY(h, cudaEventRecord(e0, h->stream));
     }
-    const dim3 grid((unsigned)(h->cfg.n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS)), block(THREADS);    // one warp per sub-tile
+    const int64_t n_ctas = h->cfg.n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS;      // one warp per sub-tile
+    const dim3 block(THREADS);
     uint32_t m = mode & ~(M_WEEKDAY | M_LOG);
     const bool pdl = h->cfg.use_pdl != 0;
+    const dim3 grid((unsigned)n_ctas);
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
 #define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_sweep_kernel<MODE>, grid, block, h->stream, pdl, h->T, h->G, w, (const DevClock*)h->clock, m))
     if (m == (M_INFECT | M_STEP | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_INCR);                       // night
@@ -410,14 +413,14 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if ((rc = alloc_zero(h, (size_t)1, &h->rows_done))) return rc;
     if ((rc = alloc_zero(h, (size_t)2 * cfg->n_districts + 8, &h->scratch))) return rc;
     {
-        // event queues: a power of two <= 2048 of them; queue q takes the events of the sweep CTAs b with
+        // event queues: a power of two <= 1024 of them; queue q takes the events of the sweep CTAs b with
         // b & q_mask == q, so its worst case (every agent of those CTAs deferred) is ceil(n_ctas / n_queues) tiles
         const int64_t n_ctas = cfg->n_tiles * (ABM_TILE / ABM_SUBTILE) / WARPS;
         uint32_t nq = 1;
-        while (nq < 2048u && (int64_t)nq * 2 <= n_ctas) nq <<= 1;
+        while (nq < 1024u && (int64_t)nq * 2 <= n_ctas) nq <<= 1;
         h->q_mask = nq - 1u;
         h->q_cap = (uint32_t)(((n_ctas + nq - 1) / nq) * (WARPS * ABM_SUBTILE));
-        if ((rc = alloc_zero(h, (size_t)nq, &h->q_count))) return rc;
+        if ((rc = alloc_zero(h, (size_t)2 * nq, &h->q_count))) return rc;
         uint4* qe = nullptr;
         CUDA_TRY(h, cudaMalloc(&qe, (size_t)nq * h->q_cap * sizeof(uint4)));
         h->owned.push_back(qe);
@@ -826,10 +829,10 @@ int abm_set_trace(abm_handle* h, int32_t n_substeps) {
     if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }     // kernel arguments change
     if (h->trace) { cudaFree(h->trace); h->trace = nullptr; h->trace_rows = 0; }
     if (n_substeps == 0) return ABM_OK;
-    const size_t words = (size_t)n_substeps * 6;
+    const size_t words = (size_t)n_substeps * ABM_TRACE_WORDS;
     CUDA_TRY(h, cudaMalloc(&h->trace, words * sizeof(unsigned long long)));
     std::vector<unsigned long long> init(words);
-    for (size_t i = 0; i < words; ++i) init[i] = (i & 1) ? 0ull : ~0ull;        // [min start, max end]
+    for (size_t i = 0; i < words; ++i) init[i] = ((i % ABM_TRACE_WORDS) & 1) ? 0ull : ~0ull;        // [min start, max end] pairs; debug words 6.. (even: min, odd: max)
     CUDA_TRY(h, cudaMemcpy(h->trace, init.data(), words * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     h->trace_rows = n_substeps;
     return ABM_OK;
@@ -838,7 +841,7 @@ int abm_set_trace(abm_handle* h, int32_t n_substeps) {
 int abm_read_trace(abm_handle* h, uint64_t* out, int32_t n_substeps) {
     if (!h || !out || n_substeps < 0 || n_substeps > h->trace_rows) return ABM_ERR_ARG;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    CUDA_TRY(h, cudaMemcpy(out, h->trace, (size_t)n_substeps * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(out, h->trace, (size_t)n_substeps * ABM_TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return ABM_OK;
 }
 

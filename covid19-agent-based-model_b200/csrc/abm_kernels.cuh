@@ -134,8 +134,9 @@ struct DevWork {
     unsigned int* rows_done;        // table-kernel rows finished in the current launch
     // event queues: sweep CTA b appends to queue b & q_mask; queue q owns entries [q * q_cap, (q + 1) * q_cap)
     uint4* q_entries;               // (slot | newly-infected << 31, flags, aux, 0)
-    uint32_t* q_count;              // [q_mask + 1] entries used; reset by the event kernel
+    uint32_t* q_count;              // [q_mask + 1][2] entries used from the front (generic) / from the back (decided leavers); reset by the event kernel
     uint32_t q_mask, q_cap;
+    uint32_t n_sub;                 // sub-tiles (warps' worth of slots) of this rank's store
     // optional timeline (abm_set_trace): [sub-step k][kernel 0 sweep / 1 events / 2 table][0 first CTA start, 1 last CTA end], ns
     unsigned long long* trace;
     int32_t trace_rows;
@@ -203,13 +204,27 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// extra stamps (debug): word w >= 6 of the sub-step's row, min or max over CTAs
+__device__ __forceinline__ void trace_point(const DevWork& Wk, int k, int w, bool is_max) {
+    if (Wk.trace && threadIdx.x == 0 && k >= 0 && k < Wk.trace_rows) {
+        unsigned long long* p = Wk.trace + (size_t)k * ABM_TRACE_WORDS + w;
+        if (is_max) atomicMax(p, global_timer_ns()); else atomicMin(p, global_timer_ns());
+    }
+}
 // one thread per CTA stamps the launch's [first start, last end] window
 __device__ __forceinline__ void trace_stamp(const DevWork& Wk, int k, int kernel, unsigned long long t_start) {
     if (Wk.trace && threadIdx.x == 0 && k >= 0 && k < Wk.trace_rows) {
-        unsigned long long* row = Wk.trace + ((size_t)k * 3 + kernel) * 2;
+        unsigned long long* row = Wk.trace + (size_t)k * ABM_TRACE_WORDS + kernel * 2;
         atomicMin(row, t_start);
         atomicMax(row + 1, global_timer_ns());
     }
+}
+
+// Ask L2 to fetch a sector and keep it (evict-last): the sweep issues this for the sectors the event kernel is going to
+// touch for a deferred agent, so that kernel's scattered reads / partial writes meet L2 instead of a burst of random
+// DRAM transactions.
+__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
 }
 
 // system-scope accesses for memory shared with peer GPUs
@@ -536,7 +551,8 @@ __device__ __forceinline__ uint32_t od_destination(const uint32_t* __restrict__ 
 // All table sums are integers, every draw is keyed by (agent, sub-step, site), so splitting the agents between the two
 // kernels cannot change a result.
 constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
-constexpr int EVENT_THREADS = 128;        // x 16 CTAs per SM at 32 registers: every queue of a busy night sub-step in ONE wave
+constexpr int EVENT_THREADS = 256;        // x 8 CTAs per SM at 32 registers: <= 1024 queues, all resident, one round on a busy night
+constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mover, leaves the district"; low 31 bits = the OD draw
 
 // Funnel loop (rare, irregular locations only): iterate a body over the agents whose bit is set in the per-lane `mask`.
 // Inside, J is the agent's index 0..3 within the lane and fj / aj are its flags / aux words.
@@ -555,22 +571,46 @@ constexpr int EVENT_THREADS = 128;        // x 16 CTAs per SM at 32 registers: e
 // queue group.  Entry = (slot | newly-infected << 31, flags, aux, 0): the hot words travel with the entry, so the event
 // kernel reads its queue coalesced and touches only the agent's cold sector.  One atomic per LANE that has anything to
 // append (few lanes do; the queues spread the atomics over up to 1024 addresses).
-#define ABM_PUSH_EVENTS(ev, newly)                                                                   \
+#define ABM_PUSH_EVENTS(ev, newly, lvm, XO)                                                          \
     if (ev) {                                                                                        \
-        const uint32_t q = blockIdx.x & Wk.q_mask;                                                   \
-        uint4* dst = Wk.q_entries + (size_t)q * Wk.q_cap + atomicAdd(Wk.q_count + q, (uint32_t)__popc(ev)); \
-        uint32_t m = (ev);                                                                           \
-        do {                                                                                         \
-            const uint32_t j = __ffs(m) - 1u;                                                        \
-            m &= m - 1u;                                                                             \
-            const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));    /* untouched */ \
-            const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                   \
-            *dst++ = make_uint4((slot0 + j) | ((((newly) >> j) & 1u) << 31), fj, aj, 0u);            \
-        } while (m);                                                                                 \
+        const uint32_t q = cta & Wk.q_mask;                                                          \
+        uint4* seg = Wk.q_entries + (size_t)q * Wk.q_cap;                                            \
+        uint32_t m = (ev) & ~(lvm);                 /* generic events: from the front */             \
+        if (m) {                                                                                     \
+            uint4* dst = seg + atomicAdd(Wk.q_count + 2u * q, (uint32_t)__popc(m));                  \
+            do {                                                                                     \
+                const uint32_t j = __ffs(m) - 1u;                                                    \
+                m &= m - 1u;                                                                         \
+                const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));    /* untouched */ \
+                const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                \
+                *dst++ = make_uint4((slot0 + j) | ((((newly) >> j) & 1u) << 31), fj, aj, 0u);        \
+                prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS);                     \
+                prefetch_l2_keep(G.flags + slot0 + j);                                               \
+                prefetch_l2_keep(G.aux + slot0 + j);                                                 \
+            } while (m);                                                                             \
+        }                                                                                            \
+        m = (ev) & (lvm);                           /* decided leavers: from the back */             \
+        if (m) {                                                                                     \
+            uint4* dst = seg + (Wk.q_cap - 1u) - atomicAdd(Wk.q_count + 2u * q + 1u, (uint32_t)__popc(m)); \
+            do {                                                                                     \
+                const uint32_t j = __ffs(m) - 1u;                                                    \
+                m &= m - 1u;                                                                         \
+                const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));                \
+                const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                \
+                *dst-- = make_uint4(slot0 + j, fj, aj, EV_LEAVER | (word_of(XO, (int)j) >> 1));      \
+                prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS);                     \
+                prefetch_l2_keep(G.flags + slot0 + j);                                               \
+                prefetch_l2_keep(G.aux + slot0 + j);                                                 \
+            } while (m);                                                                             \
+        }                                                                                            \
     }
 
+// resident CTAs per SM the register allocation aims at: 8 (32 registers, full occupancy) for the read-only night / noon
+// sweeps, 5 (48 registers) for the movement sweeps
+constexpr int sweep_min_blocks(uint32_t mode) { return (mode != RUNTIME_MODE && (mode & M_INCR)) ? 2048 / THREADS : 1280 / THREADS; }
+
 template <uint32_t MODE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, sweep_min_blocks(MODE))
 abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* clk, const uint32_t mode_rt) {
     __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
     __shared__ unsigned int s_acc[WARPS][2 * ABM_MAX_STATUS];   // per-warp home-pool pressure sums / head counts
@@ -581,12 +621,24 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
     // The event kernel may be scheduled as soon as SM resources free up (i.e. while this grid drains): it waits for
     // this grid's completion before it touches anything.
     launch_dependents();
-    const uint32_t sub = blockIdx.x * WARPS + wid;
+    // One CTA per tile.  (A persistent grid walking the tiles was measured: 40 instead of 32 registers on the night
+    // kernels, 62 instead of 48 at go-out, no faster on a quiet night and 10 % slower at the peak.)
+    const uint32_t cta = blockIdx.x;
+    const uint32_t sub = cta * WARPS + wid;
     const unsigned long long info = __ldg(T.sub_info + sub);
     const uint32_t L0 = (uint32_t)(info >> 48);                              // home district of every agent here
     const uint32_t slot0 = sub * SUB + lane * PER_LANE;
     const uint32_t A = (uint32_t)T.A;
 
+#ifdef ABM_PF_DIST
+    // L2 prefetch of the hot words of the tile ABM_PF_DIST CTAs ahead (one 128-byte line per 8 lanes)
+    if ((lane & 7) == 0 && (cta + ABM_PF_DIST) * WARPS < Wk.n_sub) {
+        const uint32_t pslot = slot0 + ABM_PF_DIST * WARPS * SUB;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(G.flags + pslot));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(G.aux + pslot));
+        if (lane == 0 && (mode_static & M_INFECT)) asm volatile("prefetch.global.L2 [%0];" ::"l"(G.hh_index + (pslot >> 2)));
+    }
+#endif
     // streaming loads / stores (evict-first): the hot words are touched once per launch and must not push the small
     // tables every warp re-reads out of L1
     const uint4 f4 = __ldcs(reinterpret_cast<const uint4*>(G.flags + slot0));
@@ -673,11 +725,13 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             const uint32_t r0 = __shfl_sync(FULL, row_thr, status_of(f0)), r1 = __shfl_sync(FULL, row_thr, status_of(f1));
             const uint32_t r2 = __shfl_sync(FULL, row_thr, status_of(f2)), r3 = __shfl_sync(FULL, row_thr, status_of(f3));
 #define ABM_OUT_THR(fj, aj, rj, tj, bit)                                                             \
-            if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {                   \
+            {                                                                                        \
                 const uint32_t lf = (fj) & LOCF;                                                     \
-                if (lf == IN_HOMEPOOL) tj = rj;                                                      \
-                else if (lf == IN_DEST) tj = ld_ca(Wk.thr_out + (cur_of(aj) * A + status_of(fj)));  \
-                else odd |= (bit);                                                                   \
+                const bool so = ((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u;     \
+                const bool dst = so && lf == IN_DEST;                                                \
+                if (so && lf == IN_HOMEPOOL) tj = rj;                                                \
+                if (dst) tj = ld_ca(Wk.thr_out + (cur_of(aj) * A + status_of(fj)));                  \
+                odd |= (so && lf != IN_HOMEPOOL && !dst) ? (bit) : 0u;                               \
             }
             ABM_OUT_THR(f0, a0, r0, t0, 1u)
             ABM_OUT_THR(f1, a1, r1, t1, 2u)
@@ -688,11 +742,12 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             // night: only travellers and the few agents of quirk Q4 are in an outside pool.  Straight-line,
             // predicated look-ups (the four loads are in flight together; no divergent loop to resolve).
 #define ABM_OUT_THR(fj, aj, tj, bit)                                                                 \
-            if (((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u) {                   \
+            {                                                                                        \
                 const uint32_t lf = (fj) & LOCF;                                                     \
-                if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL))                                   \
-                    tj = ld_ca(Wk.thr_out + ((lf == IN_DEST ? cur_of(aj) : L0) * A + status_of(fj))); \
-                else odd |= (bit);                                                                   \
+                const bool so = ((fj) & F_EPI_MASK) == EPI_S && ((fj) & (LOCF | F_BIGHH)) != 0u;     \
+                const bool reg = so && (lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL);                \
+                if (reg) tj = ld_ca(Wk.thr_out + ((lf == IN_DEST ? cur_of(aj) : L0) * A + status_of(fj))); \
+                odd |= (so && !reg) ? (bit) : 0u;                                                    \
             }
             ABM_OUT_THR(f0, a0, t0, 1u)
             ABM_OUT_THR(f1, a1, t1, 2u)
@@ -721,6 +776,8 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
     }
 
     uint32_t defer = newly;           // agents handed to the event kernel
+    uint32_t leaver = 0;              // ... of which: nothing but "mover, leaves the home district" (decided here)
+    U4 XO = U4{0u, 0u, 0u, 0u};       // OD draws of the four agents (go-out only)
     if (mode & M_STEP) {
         // ============================================================ T(k): due transitions -> event kernel
         {
@@ -732,14 +789,15 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
         // ============================================================ M(k): movement (base_model.py:274-441)
         if (mode & M_GO_HOME) {                                                         // :274-302
 #define ABM_GO_HOME(fj, aj, trj, bit)                                                                \
-            if (!(defer & (bit)) && is_active(fj)) {                                                 \
-                if ((fj) & F_AWAY) {                                                                 \
-                    if ((trj) < s.now) {                                                /* :285-293 */  \
-                        aj = ((aj) & 0xFFFF0000u) | L0;                                              \
-                        fj = (fj) & ~(F_AWAY | LOCF);                                                \
-                        dirty = true; adirty = true;                                                 \
-                    }                                                                                \
-                } else if ((fj) & LOCF) { fj &= ~LOCF; dirty = true; }          /* LOC_HOME == 0 */  \
+            {                                                                                        \
+                const bool act = !(defer & (bit)) && is_active(fj);                                  \
+                const bool away = ((fj) & F_AWAY) != 0u;                                             \
+                const bool back = act && away && (trj) < s.now;                         /* :285-293 */  \
+                const bool home = back || (act && !away);                               /* LOC_HOME == 0 */ \
+                const uint32_t nf = home ? ((fj) & ~(LOCF | (back ? F_AWAY : 0u))) : (fj);           \
+                aj = back ? (((aj) & 0xFFFF0000u) | L0) : (aj);                                      \
+                dirty |= nf != (fj); adirty |= back;                                                 \
+                fj = nf;                                                                             \
             }
             ABM_GO_HOME(f0, a0, tr0, 1u)
             ABM_GO_HOME(f1, a1, tr1, 2u)
@@ -751,17 +809,19 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             const uint32_t thr_col = (mode & M_WEEKDAY) ? 0u : 2u;
             const uint32_t od_base = ((uint32_t)s.weekday * (uint32_t)T.D + L0) * (uint32_t)T.D + L0;
             const uint32_t od_lo = L0 > 0 ? __ldg(T.od_thr + (od_base - 1u)) : 0u, od_hi = __ldg(T.od_thr + od_base);
+            const uint32_t od_span = od_hi - od_lo;       // stay-home interval [od_lo, od_hi): u - od_lo < od_span (rows are non-decreasing)
             const int64_t cid0 = (int64_t)(info & 0xFFFFFFFFFFFFull) + lane * PER_LANE;
             const U4 XM = group_draws(T, cid0, s.k, SITE_MOVER);
             uint32_t mover = 0, want_od = 0;
+            const bool mild_on = T.mild_active != 0;
 #define ABM_MOVER(fj, cls, xm, bit)                                                                  \
-            if (!(defer & (bit)) && is_active(fj)) {                                                 \
-                const bool mild = T.mild_active && ((fj) & F_ONSET) && ((fj) & F_EPI_MASK) < EPI_R;   /* :212-219, :316 */ \
+            {                                                                                        \
+                const bool act = !(defer & (bit)) && is_active(fj);                                  \
+                const bool mild = mild_on && ((fj) & F_ONSET) && ((fj) & F_EPI_MASK) < EPI_R;         /* :212-219, :316 */ \
                 const uint32_t thr = __ldg(T.move_thr + (thr_col + 4u * (cls) + (mild ? 1u : 0u)));   \
-                if (((xm) >> 1) < thr) {                                                /* :317-318 a mover */ \
-                    mover |= (bit);                                                                  \
-                    if ((fj) & F_DMOVER) want_od |= (bit);                                           \
-                }                                                                                    \
+                const bool mv = act && ((xm) >> 1) < thr;                               /* :317-318 a mover */ \
+                mover |= mv ? (bit) : 0u;                                                            \
+                want_od |= (mv && ((fj) & F_DMOVER)) ? (bit) : 0u;                                   \
             }
             ABM_MOVER(f0, mc.x & 0xFFFFu, XM.x, 1u)
             ABM_MOVER(f1, mc.x >> 16, XM.y, 2u)
@@ -771,20 +831,22 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             // District movers whose OD draw falls outside the stay-home interval of their row leave the district: the
             // destination search and the length of stay are the event kernel's.  Travellers are back in the home district
             // when the stay is over (:342-360), then like everybody else.  All other movers go about their economic activity.
-            U4 XO = U4{0u, 0u, 0u, 0u};
             if (want_od) XO = group_draws(T, cid0, s.k, SITE_OD);
 #define ABM_GO_OUT(fj, aj, trj, xo, bit)                                                             \
-            if (mover & (bit)) {                                                                     \
-                const uint32_t u = (xo) >> 1;                                                        \
-                const bool leaves = (want_od & (bit)) && !(u >= od_lo && u < od_hi);                 \
-                if (((fj) & F_AWAY) && !((trj) < s.now)) {                                           \
-                    /* away on paper, not due back: economic activity of the HOME district (quirk Q4) */ \
-                    const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf;     \
-                } else if (leaves) defer |= (bit);       /* incl. a traveller who is due back and leaves again */ \
-                else {                                                                               \
-                    if ((fj) & F_AWAY) { aj = ((aj) & 0xFFFF0000u) | L0; fj &= ~F_AWAY; dirty = true; adirty = true; } \
-                    const uint32_t nf = set_loc(fj, econ_loc(fj)); dirty |= nf != (fj); fj = nf;     \
-                }                                                                                    \
+            {                                                                                        \
+                const bool mv = (mover & (bit)) != 0u;                                               \
+                const bool away = ((fj) & F_AWAY) != 0u;                                             \
+                const bool q4 = away && !((trj) < s.now);   /* away on paper, not due back: quirk Q4 */ \
+                const bool leaves = (want_od & (bit)) && (((xo) >> 1) - od_lo) >= od_span;           \
+                const bool lv = mv && !q4 && leaves;        /* incl. a traveller who is due back and leaves again */ \
+                const bool upd = mv && !lv;                                                          \
+                const bool ret = upd && away && !q4;        /* traveller back in the home district (:342-360) */ \
+                defer |= lv ? (bit) : 0u;                                                            \
+                leaver |= (lv && !away) ? (bit) : 0u;       /* at home, untouched by I / T: fully decided */ \
+                const uint32_t nf = upd ? (set_loc(fj, econ_loc(fj)) & ~(ret ? F_AWAY : 0u)) : (fj); /* :331-339, :346-352 */ \
+                aj = ret ? (((aj) & 0xFFFF0000u) | L0) : (aj);                                       \
+                dirty |= nf != (fj); adirty |= ret;                                                  \
+                fj = nf;                                                                             \
             }
             ABM_GO_OUT(f0, a0, tr0, XO.x, 1u)
             ABM_GO_OUT(f1, a1, tr1, XO.y, 2u)
@@ -796,7 +858,7 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
         // ============================================================ A(k): pressure / headcount tables
         if (!(mode & M_INCR)) {
             unsigned long long* const acc_k = (s.k & 1) ? Wk.acc2[1] : Wk.acc2[0];
-            unsigned long long* acc_r = acc_k + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+            unsigned long long* acc_r = acc_k + (size_t)(cta & Wk.rep_mask) * (2u * T.P * A);
             unsigned long long* acc_n = acc_r + (size_t)T.P * A;
             // Home-district pool: per-warp shared accumulators (daytime) or global adds (night).  Trip
             // destinations: predicated global adds.  Schools, the hospital of district 0 (quirk Q3) and
@@ -806,38 +868,30 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             constexpr uint32_t BH_MASK = F_EPI_MASK | LOCF | F_BIGHH, BH_VAL = EPI_C | F_BIGHH;
             uint32_t work = 0;
             if (mode & M_DENSE_A) {
-                // per-lane head counts in 4-bit fields (status 0..11), widened to bytes for three warp reductions
-                unsigned long long cw = 0ull;
-                uint32_t dest = 0;
+                // per-lane head counts of the home pool in 4-bit fields (status 0..7 | 8..11), widened to bytes for
+                // three warp reductions; everybody else who is in a pool (trip destination, school, hospital of
+                // district 0) goes through the funnel
+                uint32_t cw_lo = 0, cw_hi = 0;
 #define ABM_COUNT(fj, bit)                                                                           \
-                if (!(defer & (bit))) {                                                              \
+                {                                                                                    \
                     const uint32_t lf = (fj) & LOCF;                                                 \
-                    if (lf == IN_HOMEPOOL) {                                                         \
-                        cw += 1ull << (((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu);                      \
-                        if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_w + status_of(fj), __ldg(T.rfx + rate_index(fj))); \
-                    } else if (lf == IN_DEST) dest |= (bit);                                         \
-                    else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                    const bool cnt = !(defer & (bit));                                               \
+                    const bool hp = cnt && lf == IN_HOMEPOOL;                                        \
+                    const uint32_t sh = ((fj) >> (F_STATUS_SHIFT - 2)) & 0x3Cu;         /* 4 * status */ \
+                    const uint32_t one = hp ? (1u << (sh & 31u)) : 0u;                               \
+                    cw_lo += (sh & 32u) ? 0u : one;                                                  \
+                    cw_hi += (sh & 32u) ? one : 0u;                                                  \
+                    if (hp && ((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_w + (sh >> 2), __ldg(T.rfx + rate_index(fj))); \
+                    work |= (cnt && (lf == IN_DEST || lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL)) ? (bit) : 0u; \
                 }
                 ABM_COUNT(f0, 1u)
                 ABM_COUNT(f1, 2u)
                 ABM_COUNT(f2, 4u)
                 ABM_COUNT(f3, 8u)
 #undef ABM_COUNT
-#define ABM_ADD_DEST(fj, aj, bit)                                                                    \
-                if (dest & (bit)) {                                                                  \
-                    const uint32_t e = cur_of(aj) * A + status_of(fj);                               \
-                    atomicAdd(acc_n + e, 1ull);                                                      \
-                    if (((fj) & F_EPI_MASK) == EPI_C) atomicAdd(acc_r + e, (unsigned long long)__ldg(T.rfx + rate_index(fj))); \
-                }
-                ABM_ADD_DEST(f0, a0, 1u)
-                ABM_ADD_DEST(f1, a1, 2u)
-                ABM_ADD_DEST(f2, a2, 4u)
-                ABM_ADD_DEST(f3, a3, 8u)
-#undef ABM_ADD_DEST
-                const uint32_t lo32 = (uint32_t)cw, hi32 = (uint32_t)(cw >> 32);
-                const uint32_t ev = __reduce_add_sync(FULL, lo32 & 0x0F0F0F0Fu);             // statuses 0,2,4,6
-                const uint32_t od = __reduce_add_sync(FULL, (lo32 >> 4) & 0x0F0F0F0Fu);      // statuses 1,3,5,7
-                const uint32_t hi = __reduce_add_sync(FULL, (hi32 & 0x0F0Fu) | (((hi32 >> 4) & 0x0F0Fu) << 16));   // 8,10 | 9,11
+                const uint32_t ev = __reduce_add_sync(FULL, cw_lo & 0x0F0F0F0Fu);            // statuses 0,2,4,6
+                const uint32_t od = __reduce_add_sync(FULL, (cw_lo >> 4) & 0x0F0F0F0Fu);     // statuses 1,3,5,7
+                const uint32_t hi = __reduce_add_sync(FULL, (cw_hi & 0x0F0Fu) | (((cw_hi >> 4) & 0x0F0Fu) << 16));   // 8,10 | 9,11
                 if (lane < (int)A) {
                     const uint32_t w = lane < 8 ? ((lane & 1) ? od : ev) : hi;
                     const uint32_t sh = lane < 8 ? 8u * (lane >> 1) : 8u * (((lane - 8) >> 1) + 2 * ((lane - 8) & 1));
@@ -847,10 +901,12 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
                 // night: hardly anybody is in an outside pool
                 uint32_t pooled = 0;
 #define ABM_COUNT(fj, bit)                                                                           \
-                if (!(defer & (bit))) {                                                              \
+                {                                                                                    \
                     const uint32_t lf = (fj) & LOCF;                                                 \
-                    if ((lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL)) pooled |= (bit);               \
-                    else if (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL) work |= (bit); \
+                    const bool cnt = !(defer & (bit));                                               \
+                    const bool reg = cnt && (lf - IN_HOMEPOOL) <= (IN_DEST - IN_HOMEPOOL);           \
+                    pooled |= reg ? (bit) : 0u;                                                      \
+                    work |= (cnt && (lf == IN_POOL || lf == IN_HOSP || ((fj) & BH_MASK) == BH_VAL)) ? (bit) : 0u; \
                 }
                 ABM_COUNT(f0, 1u)
                 ABM_COUNT(f1, 2u)
@@ -894,7 +950,7 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
     }
 
     // ================================================================ hand the deferred agents to the event kernel
-    ABM_PUSH_EVENTS(defer, newly)
+    ABM_PUSH_EVENTS(defer, newly, leaver, XO)
     trace_stamp(Wk, s.k, 0, t_start);
 
     // ================================================================ flush of the warp's home-pool accumulators
@@ -937,87 +993,111 @@ abm_event_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
     const uint32_t A = (uint32_t)T.A;
 
     for (uint32_t q = blockIdx.x; q <= Wk.q_mask; q += gridDim.x) {
-        const uint32_t n = ld_ca(Wk.q_count + q);
+        const uint32_t n_gen = ld_ca(Wk.q_count + 2u * q), n = n_gen + ld_ca(Wk.q_count + 2u * q + 1u);
         const uint4* entries = Wk.q_entries + (size_t)q * Wk.q_cap;
+        // generic events first, then the decided leavers: warps run one kind of body (but for the one at the boundary)
         for (uint32_t i = threadIdx.x; i < n; i += EVENT_THREADS) {
-            const uint4 e = (q == blockIdx.x && i == threadIdx.x) ? e_first : __ldcs(entries + i);
+            const uint4 e = (q == blockIdx.x && i == threadIdx.x && i < n_gen) ? e_first
+                                                                               : __ldcs(entries + (i < n_gen ? i : Wk.q_cap - 1u - (i - n_gen)));
             const uint32_t slot = e.x & 0x7FFFFFFFu;
             uint32_t f = e.y, a = e.z;
-            Cold c = load_cold(G, slot);
             const unsigned long long info = __ldg(T.sub_info + (slot >> 7));
             const int L0 = (int)(info >> 48);
             const int64_t cid = (int64_t)(info & 0xFFFFFFFFFFFFull) + (slot & (SUB - 1));
             const int J = (int)(slot & 3u);                     // word of the group Philox blocks that is this agent's
-            bool cold_dirty = false;
-            if (e.x >> 31) {                                     // I(k-1): the draw infected this agent
-                f = infect_agent(T, f, a, c, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
-                atomicAdd(s_tally + CUM_INFECTED, 1);
-                cold_dirty = true;
-            }
-            if (mode & M_STEP) {
-                if ((a >> 16) <= (uint32_t)s.k) {                // T(k)
-                    if (mode & M_INCR) {
-                        DeltaSink sink;
-                        sink.acc_r = ((s.k & 1) ? Wk.acc2[1] : Wk.acc2[0]) + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
-                        sink.acc_n = sink.acc_r + (size_t)T.P * A;
-                        sink.hbig = (s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
-                        sink.L0 = L0; sink.cid = cid;
-                        f = transition_agent(T, G, f, a, slot, c, s.now, s_tally, &sink);
-                    } else {
-                        f = transition_agent(T, G, f, a, slot, c, s.now, s_tally);
-                    }
+            if (e.w & EV_LEAVER) {
+                // The sweep already decided: an active mover at home whose OD draw leaves the district (:366-441), no
+                // infection, no due event.  Destination, length of stay; the cold sector is only written (one word).
+                const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
+                const uint32_t dest = od_destination(od_row, T.D, e.w & 0x7FFFFFFFu);
+                if (dest != (uint32_t)L0) {                                             // :410-439
+                    const uint32_t xs = word_of(group_draws(T, cid, s.k, SITE_STAY), J);
+                    G.cold[(size_t)slot * ABM_COLD_WORDS + ABM_COLD_T_RETURN] = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
+                    f = set_loc(f, LOC_DEST) | F_AWAY;
+                    a = (a & 0xFFFF0000u) | dest;
+                } else {
+                    f = set_loc(f, econ_loc(f));
                 }
-                if ((mode & M_GO_HOME) && is_active(f)) {                               // base_model.py:274-302
-                    if (f & F_AWAY) {
-                        if (c.u.x < s.now) {                                            // :285-293
-                            a = (a & 0xFFFF0000u) | (uint32_t)L0;
-                            f &= ~(F_AWAY | LOCF);
-                        }
-                    } else {
-                        f &= ~LOCF;                                                     // LOC_HOME == 0
-                    }
+            } else {
+                Cold c = load_cold(G, slot);
+                bool cold_dirty = false;
+                if (e.x >> 31) {                                     // I(k-1): the draw infected this agent
+                    f = infect_agent(T, f, a, c, cid, s.k_inf, s.now_inf, (uint32_t)s.k_inf + 1u, s_tally);
+                    atomicAdd(s_tally + CUM_INFECTED, 1);
+                    cold_dirty = true;
                 }
-                if ((mode & M_GO_OUT) && is_active(f)) {                                // :304-340
-                    const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;     // :212-219, :316
-                    const uint32_t cls = G.move_class[slot];
-                    const uint32_t thr = __ldg(T.move_thr + (((mode & M_WEEKDAY) ? 0u : 2u) + 4u * cls + (mild ? 1u : 0u)));
-                    const uint32_t xm = word_of(group_draws(T, cid, s.k, SITE_MOVER), J);
-                    if ((xm >> 1) < thr) {                                              // :317-318 a mover
-                        const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
-                        uint32_t u = 0;
-                        bool leaves = false;
-                        if (f & F_DMOVER) {
-                            u = word_of(group_draws(T, cid, s.k, SITE_OD), J) >> 1;
-                            const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
-                            leaves = !(u >= od_lo && u < od_hi);
+                if (mode & M_STEP) {
+                    if ((a >> 16) <= (uint32_t)s.k) {                // T(k)
+                        if (mode & M_INCR) {
+                            DeltaSink sink;
+                            sink.acc_r = ((s.k & 1) ? Wk.acc2[1] : Wk.acc2[0]) + (size_t)(blockIdx.x & Wk.rep_mask) * (2u * T.P * A);
+                            sink.acc_n = sink.acc_r + (size_t)T.P * A;
+                            sink.hbig = (s.k & 1) ? Wk.hbig2[1] : Wk.hbig2[0];
+                            sink.L0 = L0; sink.cid = cid;
+                            f = transition_agent(T, G, f, a, slot, c, s.now, s_tally, &sink);
+                        } else {
+                            f = transition_agent(T, G, f, a, slot, c, s.now, s_tally);
                         }
-                        bool go = false;
+                    }
+                    if ((mode & M_GO_HOME) && is_active(f)) {                               // base_model.py:274-302
                         if (f & F_AWAY) {
-                            // travellers: back in the home district when the stay is over (:342-360), then like everybody else
-                            if (c.u.x < s.now) {
+                            if (c.u.x < s.now) {                                            // :285-293
                                 a = (a & 0xFFFF0000u) | (uint32_t)L0;
-                                f &= ~F_AWAY;
-                                go = leaves;
+                                f &= ~(F_AWAY | LOCF);
                             }
                         } else {
-                            go = leaves;
+                            f &= ~LOCF;                                                     // LOC_HOME == 0
                         }
-                        bool econ = !go;
-                        if (go) {                                                       // :366-441
-                            const uint32_t dest = od_destination(od_row, T.D, u);
-                            if (dest != (uint32_t)L0) {                                 // :410-439
-                                const uint32_t xs = word_of(group_draws(T, cid, s.k, SITE_STAY), J);
-                                c.u.x = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
-                                cold_dirty = true;
-                                f = set_loc(f, LOC_DEST) | F_AWAY;
-                                a = (a & 0xFFFF0000u) | dest;
-                            } else {
-                                econ = true;
+                    }
+                    if ((mode & M_GO_OUT) && is_active(f)) {                                // :304-340
+                        const bool mild = T.mild_active && (f & F_ONSET) && (f & F_EPI_MASK) < EPI_R;     // :212-219, :316
+                        const uint32_t cls = G.move_class[slot];
+                        const uint32_t thr = __ldg(T.move_thr + (((mode & M_WEEKDAY) ? 0u : 2u) + 4u * cls + (mild ? 1u : 0u)));
+                        const uint32_t xm = word_of(group_draws(T, cid, s.k, SITE_MOVER), J);
+                        if ((xm >> 1) < thr) {                                              // :317-318 a mover
+                            const uint32_t* od_row = T.od_thr + ((size_t)s.weekday * T.D + L0) * T.D;
+                            uint32_t u = 0;
+                            bool leaves = false;
+                            if (f & F_DMOVER) {
+                                u = word_of(group_draws(T, cid, s.k, SITE_OD), J) >> 1;
+                                const uint32_t od_lo = L0 > 0 ? __ldg(od_row + L0 - 1) : 0u, od_hi = __ldg(od_row + L0);
+                                leaves = !(u >= od_lo && u < od_hi);
                             }
+                            bool go = false;
+                            if (f & F_AWAY) {
+                                // travellers: back in the home district when the stay is over (:342-360), then like everybody else
+                                if (c.u.x < s.now) {
+                                    a = (a & 0xFFFF0000u) | (uint32_t)L0;
+                                    f &= ~F_AWAY;
+                                    go = leaves;
+                                }
+                            } else {
+                                go = leaves;
+                            }
+                            bool econ = !go;
+                            if (go) {                                                       // :366-441
+                                const uint32_t dest = od_destination(od_row, T.D, u);
+                                if (dest != (uint32_t)L0) {                                 // :410-439
+                                    const uint32_t xs = word_of(group_draws(T, cid, s.k, SITE_STAY), J);
+                                    c.u.x = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
+                                    cold_dirty = true;
+                                    f = set_loc(f, LOC_DEST) | F_AWAY;
+                                    a = (a & 0xFFFF0000u) | dest;
+                                } else {
+                                    econ = true;
+                                }
+                            }
+                            if (econ) f = set_loc(f, econ_loc(f));                          // :331-339, :346-352
                         }
-                        if (econ) f = set_loc(f, econ_loc(f));                          // :331-339, :346-352
                     }
                 }
+                if (cold_dirty) {
+                    int4* p = reinterpret_cast<int4*>(G.cold) + (size_t)slot * 2;
+                    p[0] = c.t;
+                    p[1] = c.u;
+                }
+            }
+            if (mode & M_STEP) {
                 if (!(mode & M_INCR)) {                                                 // A(k) of this one agent
                     const Contribution cb = contribution_of(G, f, a, slot, L0);
                     if (cb.pool >= 0) {
@@ -1033,14 +1113,9 @@ abm_event_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
             }
             G.flags[slot] = f;
             G.aux[slot] = a;
-            if (cold_dirty) {
-                int4* p = reinterpret_cast<int4*>(G.cold) + (size_t)slot * 2;
-                p[0] = c.t;
-                p[1] = c.u;
-            }
         }
         __syncthreads();                  // every thread has read the count
-        if (threadIdx.x == 0) Wk.q_count[q] = 0u;
+        if (threadIdx.x < 2) Wk.q_count[2u * q + threadIdx.x] = 0u;
     }
     __syncthreads();
     if (threadIdx.x < N_TALLY) {

@@ -33,6 +33,7 @@ extern "C" {
 #define ABM_LOG_STRIDE 16        /* int64 words per day-log row                                    */
 #define ABM_MAX_RANKS 16         /* ranks of one node that can share tables through peer memory    */
 #define ABM_IPC_HANDLE_BYTES 64  /* size of the opaque handle abm_peer_export produces             */
+#define ABM_TRACE_WORDS 12       /* uint64 words per sub-step of the device-side timeline            */
 #define ABM_COLD_WORDS 8         /* int32 words of an agent's cold (event-time) record              */
 #define ABM_COLD_T_INFECTED 0
 #define ABM_COLD_T_CONTAGIOUS 1
@@ -173,7 +174,8 @@ int abm_table_time(abm_handle* h, double* total_ms);
 int abm_event_time(abm_handle* h, double* total_ms);
 /* Device-side timeline (measurement only): after abm_set_trace(h, n) every kernel of sub-steps 0..n-1 stamps the
  * window [first CTA start, last CTA end] of its launch with the GPU's global nanosecond timer; abm_read_trace copies
- * n rows of 6 uint64 (sweep start, end, event kernel start, end, table kernel start, end).  n = 0 switches it off. */
+ * n rows of ABM_TRACE_WORDS uint64 (sweep start, end, event kernel start, end, table kernel start, end, then
+ * kernel-internal debug stamps).  n = 0 switches it off. */
 int abm_set_trace(abm_handle* h, int32_t n_substeps);
 int abm_read_trace(abm_handle* h, uint64_t* out, int32_t n_substeps);
 /* Checkpoint / resume (the reference pickles the whole model, scenario_models.py:497-500): the agent

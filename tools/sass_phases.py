@@ -42,8 +42,13 @@ def phase_marks(src):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith('--')]
-    top = int(sys.argv[sys.argv.index('--lines') + 1]) if '--lines' in sys.argv else 12
+    argv = list(sys.argv[1:])
+    if '--lines' in argv:
+        j = argv.index('--lines'); top_arg = argv[j + 1]; del argv[j:j + 2]
+    else:
+        top_arg = '12'
+    args = [a for a in argv if not a.startswith('--')]
+    top = int(top_arg)
     mode = args[0] if args else '259'
     lib = args[1] if len(args) > 1 else os.path.join(ROOT, 'covid19-agent-based-model_b200', 'libabm_b200.so')
     tmp = tempfile.mkdtemp(prefix='sass_')

@@ -36,6 +36,7 @@ sim.step(a.spinup * 6)
 torch.cuda.synchronize()
 sim.step(a.days * 6)
 tr = sim.read_trace(n_sub).astype(np.int64)
+dbg = sim.trace_debug.astype(np.int64)
 k0 = (a.spinup + 1) * 6          # skip the first traced day after the spin-up boundary
 print('sub-step  hour | sweep  gap  events  gap  table  gap->next | total   (us)')
 tot = []
@@ -43,6 +44,6 @@ for k in range(k0, n_sub - 1):
     sw, ev, tb, nxt = tr[k, 0], tr[k, 1], tr[k, 2], tr[k + 1, 0]
     row = [(sw[1] - sw[0]), (ev[0] - sw[1]), (ev[1] - ev[0]), (tb[0] - ev[1]), (tb[1] - tb[0]), (nxt[0] - tb[1]), (nxt[0] - sw[0])]
     tot.append(row)
-    print(f'{k:7d}  {(k * 4) % 24:4d} | ' + '  '.join(f'{v / 1e3:6.1f}' for v in row))
+    print(f'{k:7d}  {(k * 4) % 24:4d} | ' + '  '.join(f'{v / 1e3:6.1f}' for v in row) + '   dbg(rel. sweep end): ' + ' '.join(f'{(d - sw[1]) / 1e3:6.1f}' for d in (dbg[k, 0], dbg[k, 1], dbg[k, 5], tr[k, 2, 1], dbg[k, 2], dbg[k, 3])))
 m = np.array(tot, dtype=float).mean(0) / 1e3
 print('mean          | ' + '  '.join(f'{v:6.1f}' for v in m))
