@@ -54,7 +54,7 @@ COLD_FIELDS = ('t_infected', 't_contagious', 't_onset', 't_recovered', 't_return
 
 
 EXPORTS = ['abm_create', 'abm_set_tables', 'abm_bind_agents', 'abm_refresh', 'abm_seed', 'abm_step', 'abm_flush',
-           'abm_read_log', 'abm_counters', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
+           'abm_read_log', 'abm_counters', 'abm_active_infections', 'abm_district_symptomatic', 'abm_debug_tables', 'abm_set_profiling',
            'abm_kernel_time', 'abm_table_time', 'abm_event_time', 'abm_set_trace', 'abm_read_trace', 'abm_get_state', 'abm_set_state', 'abm_current_step', 'abm_launch_count', 'abm_sync', 'abm_last_error', 'abm_destroy',
            'abm_version', 'abm_nccl_unique_id', 'abm_peer_export', 'abm_peer_attach', 'abm_peer_detach']
 
@@ -82,6 +82,7 @@ def load_library(path=LIB_PATH):
     lib.abm_flush.argtypes = [vp]
     lib.abm_read_log.argtypes = [vp, vp, ct.c_int32, ct.POINTER(ct.c_int32)]
     lib.abm_counters.argtypes = [vp, vp]
+    lib.abm_active_infections.argtypes = [vp, ct.POINTER(ct.c_int64)]
     lib.abm_district_symptomatic.argtypes = [vp, vp, vp]
     lib.abm_debug_tables.argtypes = [vp, vp, vp, vp]
     lib.abm_set_profiling.argtypes = [vp, ct.c_int32]
@@ -341,6 +342,13 @@ class Simulation:
         out = np.zeros(12, dtype=np.int64)
         self._check(self.lib.abm_counters(self.h, _ptr(out)))
         return {name: int(out[i]) for i, name in enumerate(COUNTER_NAMES)}
+
+    def active_infections(self):
+        """Exposed + contagious agents of this rank from the running device counters: run_scenario's stop test
+        (scenario_models.py:494-495) without a flush and without a kernel launch."""
+        n = ct.c_int64()
+        self._check(self.lib.abm_active_infections(self.h, ct.byref(n)))
+        return int(n.value)
 
     def district_symptomatic(self):
         D = self.spec.n_districts

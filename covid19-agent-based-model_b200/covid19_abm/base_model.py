@@ -649,8 +649,7 @@ class Country:
         if self._sim is None:
             s = self._host['epidemic_state']
             return int(((s >= self.STATE_INFECTED) & (s < self.STATE_RECOVERED)).sum())
-        c = self._sim.counters()
-        return c['current_exposed_cases'] + c['current_contagious_cases']
+        return self._sim.active_infections()      # running device counters: no flush, the fused launch sequence stays
 
     # ------------------------------------------------------------------ infection (base_model.py:838-1055)
     def set_epidemic_status(self, neighbors_to_infect):

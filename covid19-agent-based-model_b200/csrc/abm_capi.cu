@@ -281,6 +281,22 @@ int enqueue_substep(abm_handle* h, const SubstepPlan& p, int64_t* launches) {
     return ABM_OK;
 }
 
+// A peer that did not publish its table rows in time (abm_hazard_table_kernel gives up after a bounded wait so a dead
+// peer cannot hang the GPU) leaves the thresholds of that sub-step at zero and raises a device flag; the host reads it
+// at every call that synchronises anyway.  Sticky: the trajectory is no longer the single-rank one.
+int check_exchange(abm_handle* h) {
+    if (h->exchange_failed) return fail(h, ABM_ERR_STATE, "table exchange failed earlier: a peer rank did not publish its rows in time");
+    if (!h->peers_attached) return ABM_OK;
+    int32_t flag = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&flag, &h->clock->xchg_error, sizeof flag, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        h->exchange_failed = true;
+        return fail(h, ABM_ERR_STATE, "table exchange failed: a peer rank did not publish its rows in time (rank %d of %d)", h->cfg.rank, h->cfg.world_size);
+    }
+    return ABM_OK;
+}
+
 int check_limits(abm_handle* h, int64_t k_after, int32_t logs_after) {
     const abm_config& c = h->cfg;
     if (k_after >= 0xFFF0) return fail(h, ABM_ERR_STATE, "sub-step index exceeds the 16-bit event field");
@@ -559,6 +575,7 @@ int abm_seed(abm_handle* h, const int64_t* slots, const int64_t* ids, int64_t n)
 int abm_step(abm_handle* h, int32_t n_substeps) {
     if (!h || n_substeps < 0) return ABM_ERR_ARG;
     if (!h->have_tables || !h->have_agents) return fail(h, ABM_ERR_STATE, "tables / agents not set");
+    if (h->exchange_failed) return fail(h, ABM_ERR_STATE, "table exchange failed earlier: a peer rank did not publish its rows in time");
     const abm_config& c = h->cfg;
     const bool periodic = 1440 % c.step_ticks == 0;
     const int spd = periodic ? 1440 / c.step_ticks : 0;
@@ -614,7 +631,7 @@ int abm_flush(abm_handle* h) {
 int abm_sync(abm_handle* h) {
     if (!h) return ABM_ERR_ARG;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return ABM_OK;
+    return check_exchange(h);
 }
 
 int abm_read_log(abm_handle* h, int64_t* out, int32_t max_rows, int32_t* n_rows) {
@@ -623,15 +640,14 @@ int abm_read_log(abm_handle* h, int64_t* out, int32_t max_rows, int32_t* n_rows)
     CUDA_TRY(h, cudaMemcpyAsync(out, h->daylog, (size_t)n * ABM_LOG_STRIDE * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *n_rows = n;
-    return ABM_OK;
+    return check_exchange(h);
 }
 
 int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
     if (!h || !out) return ABM_ERR_ARG;
     int rc = abm_flush(h);
     if (rc) return rc;
-    unsigned long long* d4 = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d4, 4 * sizeof(unsigned long long)));
+    unsigned long long* d4 = h->scratch;
     CUDA_TRY(h, cudaMemsetAsync(d4, 0, 4 * sizeof(unsigned long long), h->stream));
     const int64_t n = h->cfg.n_slots;
     abm_count_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->G, n, d4);
@@ -642,7 +658,7 @@ int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
     CUDA_TRY(h, cudaMemcpyAsync(pend.data(), h->tally, pend.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(run, h->counters, sizeof run, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d4);
+    if ((rc = check_exchange(h))) return rc;
     for (int i = 0; i < 8; ++i) {       // tallies of a flush are folded by the next table kernel
         cum[i] = run[i];
         for (int r = 0; r < h->replicas; ++r) cum[i] += (long long)pend[(size_t)r * N_TALLY + i];
@@ -669,20 +685,30 @@ int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]) {
     return ABM_OK;
 }
 
+int abm_active_infections(abm_handle* h, int64_t* out) {
+    if (!h || !out) return ABM_ERR_ARG;
+    // running counters 8, 9 = exposed, contagious after the transitions of the last executed sub-step; the infection
+    // draw of that sub-step is still pending, but it cannot infect anybody when nobody is contagious, so `== 0` means
+    // what the reference's test on the state vector means -- and the fused launch sequence stays intact (no flush)
+    long long cur[2];
+    CUDA_TRY(h, cudaMemcpyAsync(cur, h->counters + 8, sizeof cur, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = (int64_t)(cur[0] + cur[1]);
+    return check_exchange(h);
+}
+
 int abm_district_symptomatic(abm_handle* h, int64_t* sym, int64_t* pop) {
     if (!h || !sym || !pop) return ABM_ERR_ARG;
     int rc = abm_flush(h);
     if (rc) return rc;
     const int D = h->cfg.n_districts;
-    unsigned long long* d = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d, 2 * D * sizeof(unsigned long long)));
+    unsigned long long* d = h->scratch + 8;
     CUDA_TRY(h, cudaMemsetAsync(d, 0, 2 * D * sizeof(unsigned long long), h->stream));
     const int64_t n = h->cfg.n_slots;
     abm_district_sym_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->T, h->G, n, d, d + D);
     CUDA_TRY(h, cudaMemcpyAsync(sym, d, D * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(pop, d + D, D * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d);
     h->launches++;
     return ABM_OK;
 }
@@ -744,15 +770,33 @@ int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTER
     run[CUM_ASYM] = counters[ABM_C_ASYMPTOMATIC_COUNT];
     run[CUM_SYM] = counters[ABM_C_SYMPTOMATIC_COUNT];
     for (int i = 0; i < 4; ++i) run[8 + i] = counters[ABM_C_CURRENT_EXPOSED_CASES + i];
+    // Valid on a handle that has already run: the generation of the peer exchange is kept (peers compare their flags
+    // against it), every accumulator that carries state from one sub-step to the next is cleared, and the day graph is
+    // dropped (it was captured for another phase of the day).
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     DevClock clk{};
+    CUDA_TRY(h, cudaMemcpy(&clk, h->clock, sizeof clk, cudaMemcpyDeviceToHost));
+    const uint32_t keep_gen = clk.xchg_gen;
+    clk = DevClock{};
+    clk.xchg_gen = keep_gen;
     clk.k = (int32_t)k; clk.now = (int32_t)(k * c.step_ticks);
     clk.minute_abs = c.start_minute_of_day + clk.now; clk.weekday0 = c.start_weekday;
     clk.weekday = (c.start_weekday + clk.minute_abs / 1440) % 7;
     clk.n_log_rows = 0; clk.seeds_before = seeded; clk.seeds_at_now = 0;
+    const size_t pa = (size_t)c.n_pools * c.n_status;
     CUDA_TRY(h, cudaMemcpyAsync(h->clock, &clk, sizeof clk, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->counters, run, sizeof run, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->tally, 0, (size_t)h->replicas * N_TALLY * sizeof(unsigned long long), h->stream));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(h, cudaMemsetAsync(h->acc[b], 0, (size_t)h->replicas * 2 * pa * sizeof(unsigned long long), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(h->hbig[b], 0, ((size_t)c.n_big_households + 1) * sizeof(unsigned long long), h->stream));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->acc_local, 0, 2 * pa * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->acc_sum, 0, 2 * pa * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->rows_done, 0, sizeof(unsigned int), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->q_count, 0, (size_t)2 * (h->q_mask + 1u) * sizeof(uint32_t), h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->day_graph) { cudaGraphExecDestroy(h->day_graph); h->day_graph = nullptr; }
     h->k = k;
     h->n_log_rows = 0;
     h->pending_infect = false;

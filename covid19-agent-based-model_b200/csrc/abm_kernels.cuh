@@ -1152,6 +1152,8 @@ __global__ void __launch_bounds__(TABLE_THREADS)
 abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restrict__ clk, const TableArgs ta) {
     __shared__ unsigned long long s_part[TABLE_THREADS / 32][32];
     __shared__ unsigned long long s_row[2 * ABM_MAX_STATUS];
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
     const int A = T.A, n = T.P * A, t = threadIdx.x;
     const int L = blockIdx.x;
     const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;
@@ -1216,7 +1218,9 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
                     const unsigned int* flag = reinterpret_cast<const unsigned int*>(Wk.xchg[r] + flag_words) + (gen & 1u) * T.P + L;
                     int spins = 0;
                     while ((int)(ld_acquire_sys(flag) - gen) < 0) {
-                        if (++spins > (1 << 22)) { clk->xchg_error = 1; break; }     // a peer is gone: do not hang the GPU
+                        // a peer is gone: do not hang the GPU, but never use its stale rows either -- raise the (sticky)
+                        // flag the host checks at every synchronising call; this row's thresholds become zero below
+                        if (++spins > (1 << 22)) { atomicExch(&clk->xchg_error, 1); s_timeout = 1; break; }
                         __nanosleep(64);
                     }
                 }
@@ -1247,6 +1251,7 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
                                                                                : __double2ull_rz(__dmul_rn(lam, 4294967296.0));
                 thr = hazard_threshold_fx(T.omexp, h);
             }
+            if (s_timeout) thr = 0;              // partial sums over ranks must not infect anybody
             Wk.thr_out[L * A + t] = thr;
         }
         __syncthreads();

@@ -159,6 +159,11 @@ int abm_flush(abm_handle* h);
 int abm_read_log(abm_handle* h, int64_t* out, int32_t max_rows, int32_t* n_rows);
 /* The 12 counters at the current time, over this rank's agents (synchronises, flushes). */
 int abm_counters(abm_handle* h, int64_t out[ABM_N_COUNTERS]);
+/* run_scenario's stop test `epidemic_state in (INFECTED, CONTAGIOUS)).any()` (scenario_models.py:494-495): exposed +
+ * contagious agents after the transitions of the last executed sub-step, from the running device counters.  Synchronises
+ * but launches nothing and does NOT flush, so a driver loop that calls it after every step() keeps the fused launch
+ * sequence; 0 if and only if the reference's test is false. */
+int abm_active_infections(abm_handle* h, int64_t* out);
 /* Country.get_safe_and_unsafe_districts inputs (base_model.py:733-758): per home district, number of
  * symptomatic infected/contagious agents and population, over this rank's agents. */
 int abm_district_symptomatic(abm_handle* h, int64_t* sym, int64_t* pop);
@@ -182,12 +187,14 @@ int abm_read_trace(abm_handle* h, uint64_t* out, int32_t n_substeps);
  * vectors are the caller's buffers; these two calls carry the rest -- the clock, the 12 running counters
  * and the number of seeded infections.  abm_get_state applies pending draws first (abm_flush). */
 int abm_get_state(abm_handle* h, int64_t* k, int64_t counters[ABM_N_COUNTERS], int64_t* seeded);
-int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTERS], int64_t seeded);
+int abm_set_state(abm_handle* h, int64_t k, const int64_t counters[ABM_N_COUNTERS], int64_t seeded);   /* also valid on a handle that has run */
 /* scheduler.steps (base_model.py:177): sub-steps enqueued so far. */
 int64_t abm_current_step(abm_handle* h);
 /* Kernels launched by this handle so far (graph replays count their nodes); for bench.py's `gpu_launches`. */
 int64_t abm_launch_count(abm_handle* h);
-/* Wait for everything enqueued on the handle's stream (the reference's step() is synchronous; abm_step is not). */
+/* Wait for everything enqueued on the handle's stream (the reference's step() is synchronous; abm_step is not).
+ * Like every synchronising call it returns ABM_ERR_STATE (sticky) when a peer rank failed to publish its table rows
+ * in time during a multi-GPU sub-step. */
 int abm_sync(abm_handle* h);
 /* Message of the last failed call on this handle (every entry point returns 0 or a negative abm_status). */
 const char* abm_last_error(abm_handle* h);

@@ -78,6 +78,9 @@ class FakeSimulation:
         c = self.ora.counters(self.ora.now())
         return {k: c[k] for k in COUNTER_NAMES}
 
+    def active_infections(self):
+        return int(np.isin(self.ora.epidemic_state, [1, 2]).sum())
+
     def district_symptomatic(self):
         o = self.ora
         sick = np.isin(o.epidemic_state, [1, 2]) & (o.infected_symptomatic_status == 1)

@@ -29,6 +29,8 @@ def main():
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'])
     ap.add_argument('--shards', default='contiguous', choices=['contiguous', 'dealt'],
                     help='contiguous ranges of the canonical order, or one piece of every district per rank')
+    ap.add_argument('--lost-peer', action='store_true',
+                    help='rank 1 never steps: rank 0 must get an error from its next synchronising call, not partial sums')
     a = ap.parse_args()
 
     import torch
@@ -62,6 +64,27 @@ def main():
                          world_size=world, rank=rank, nccl_unique_id=uid, max_days=a.days + 4,
                          exchange=a.exchange if world > 1 else None)
     sim.seed_infections(seeds[np.isin(seeds, idx)])
+    if a.lost_peer:
+        # a peer that does not publish its table rows: the bounded wait in the table kernel ends, the thresholds of the
+        # sub-step are zero, and every synchronising call reports it (sticky)
+        ok = True
+        if rank == 0:
+            sim.step(1)
+            errors = []
+            for call in (sim.sync, sim.read_log, sim.counters, lambda: sim.step(1)):
+                try:
+                    call()
+                    errors.append(None)
+                except RuntimeError as e:
+                    errors.append(str(e))
+            ok = all(e is not None and 'table exchange failed' in e for e in errors)
+            print('lost peer:', errors, flush=True)
+        flag = torch.tensor([0 if ok else 1], device=device)
+        dist.all_reduce(flag)
+        if rank == 0 and int(flag.item()) == 0:
+            print('multi_gpu_check ok (lost peer reported)', flush=True)
+        sys.stdout.flush()
+        os._exit(int(flag.item()))
     sim.step(6 * a.days)
 
     ora = OracleModel(pop, dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob), tab, 4242)

@@ -105,3 +105,54 @@ def test_debug_tables_need_a_step_and_unknown_exchange_is_rejected(built_library
     sim.close()
     with pytest.raises(ValueError, match='unknown exchange'):
         Simulation(spec, pop, seed=1, tables=tab, exchange='mpi')
+
+
+@pytest.mark.parametrize('k_ckpt,k_used', [(9, 17), (10, 16), (12, 6)])
+def test_restore_onto_a_handle_that_has_already_run(built_library, k_ckpt, k_used):
+    """abm_set_state is the general resume call (include/abm_b200.h): restoring a checkpoint onto a handle that has
+    executed other sub-steps -- same or different parity of the sub-step index, mid-day or not -- continues exactly like
+    the uninterrupted run (stale accumulators / a reset exchange generation used to leak in)."""
+    from abm_b200.engine import Simulation
+    spec, pop, seeds, tab = small_case(n_agents=20_000, n_districts=5, infect_num=400)
+    ref = Simulation(spec, pop, seed=21, tables=tab, max_days=12)
+    ref.seed_infections(seeds)
+    ref.step(k_ckpt)
+    ck = ref.checkpoint()
+    ref.step(30)
+    want, want_tables = ref.state(), ref.debug_tables()
+
+    used = Simulation(spec, pop, seed=21, tables=tab, max_days=12)
+    used.seed_infections(seeds[: len(seeds) // 2])       # a different history on this handle
+    used.step(k_used)
+    used.restore(ck)
+    assert used.step_index == k_ckpt
+    used.step(30)
+    assert_state_equal(used.state(), want, where=f'restored at {k_ckpt} onto a handle at {k_used}')
+    for g, w in zip(used.debug_tables(), want_tables):
+        assert np.array_equal(g, w)
+    ref.close(); used.close()
+
+
+def test_active_infections_is_the_stop_test_without_a_flush(built_library):
+    """abm_active_infections (run_scenario's stop test, scenario_models.py:494-495): agrees with the flushed state on
+    zero / non-zero after every sub-step, launches nothing and leaves the infection draw pending."""
+    from abm_b200.engine import Simulation
+    spec, pop, seeds, tab = small_case(n_agents=5_000, n_districts=3, infect_num=3, R0=0.3)
+    sim = Simulation(spec, pop, seed=3, tables=tab, max_days=80)
+    twin = Simulation(spec, pop, seed=3, tables=tab, max_days=80)
+    assert sim.active_infections() == 0
+    sim.seed_infections(seeds); twin.seed_infections(seeds)
+    seen_zero = False
+    for k in range(6 * 70):
+        sim.step(1); twin.step(1)
+        launches = sim.launch_count
+        n = sim.active_infections()
+        assert sim.launch_count == launches
+        epi = np.asarray(twin.state()['epidemic_state'])          # flushes the twin: the reference's view
+        assert (n == 0) == (not np.isin(epi, [1, 2]).any()), k
+        if n == 0:
+            seen_zero = True
+            break
+    assert seen_zero, 'the sub-critical epidemic should have died out'
+    assert_state_equal(sim.state(), twin.state(), where='unflushed vs flushed every sub-step')
+    sim.close(); twin.close()
