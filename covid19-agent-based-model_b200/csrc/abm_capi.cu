@@ -44,7 +44,7 @@ struct abm_handle {
     bool tables_valid = false;                         // acc_local / hbig hold the sums of sub-step k - 1
     int n_sms = 1;
     // peer-memory exchange
-    unsigned long long* xchg_self = nullptr;           // exported buffer: data [2][2][P][A] u64, flags [2][P] u32
+    unsigned long long* xchg_self = nullptr;           // exported buffer the peers push their table rows into (16-byte elements)
     unsigned long long* xchg[ABM_MAX_RANKS] = {};      // every rank's buffer as mapped in this process
     bool peers_attached = false;
     unsigned int* rows_done = nullptr;
@@ -453,7 +453,7 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     if (cfg->world_size > 1 && cfg->exchange == 1) {
         if (cfg->world_size > ABM_MAX_RANKS) return fail(h, ABM_ERR_ARG, "peer exchange supports at most %d ranks", ABM_MAX_RANKS);
         // exported to the peers with cudaIpcGetMemHandle: its own allocation (not part of `owned`, freed after detach)
-        const size_t words = (size_t)4 * pa + ((size_t)2 * cfg->n_pools * sizeof(unsigned int) + 7) / 8;
+        const size_t words = (size_t)2 * cfg->world_size * 2 * pa * 2;      // [2 parities][ranks][2][P][A] elements of two 64-bit words
         CUDA_TRY(h, cudaMalloc(&h->xchg_self, words * sizeof(unsigned long long)));
         CUDA_TRY(h, cudaMemsetAsync(h->xchg_self, 0, words * sizeof(unsigned long long), h->stream));
     } else if (cfg->world_size > 1) {

@@ -129,7 +129,7 @@ struct DevWork {
     uint32_t rep_mask;
     int32_t max_log_rows;
     // multi-GPU exchange through peer memory (one node, NVLink / NVSwitch): every rank owns an exchange buffer
-    // that its peers map; layout in 64-bit words: data [2 parities][2][P][A], then 32-bit flags [2 parities][P]
+    // that its peers WRITE their rows into: [2 parities][n_ranks sources][2][P][A] elements of 16 bytes (see the table kernel)
     unsigned long long* xchg[ABM_MAX_RANKS];   // xchg[r] = rank r's buffer as mapped here (own buffer at index `rank`)
     unsigned int* rows_done;        // table-kernel rows finished in the current launch
     // event queues: sweep CTA b appends to queue b & q_mask; queue q owns entries [q * q_cap, (q + 1) * q_cap)
@@ -234,6 +234,15 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// 16-byte accesses that always go to memory (peer or local), never to a cached copy
+__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
@@ -1197,38 +1206,49 @@ abm_hazard_table_kernel(const DevTables T, const DevWork Wk, DevClock* __restric
                 Wk.acc_local[off] = sum;
                 Wk.acc_sum[off] = sum;
                 s_row[t] = sum;
-                if (Wk.n_ranks > 1) Wk.xchg[Wk.rank][(size_t)(gen & 1u) * 2 * n + off] = sum;
             }
         } else if (t < 2 * A) {
             s_row[t] = Wk.acc_sum[off];
         }
         if (Wk.n_ranks > 1 && ta.do_reduce) {
-            // ---- sum over ranks through peer memory
-            const size_t flag_words = (size_t)4 * n;                    // flags start after the two data parities
-            __threadfence_system();
-            __syncthreads();
-            if (t == 0)
-                st_release_sys(reinterpret_cast<unsigned int*>(Wk.xchg[Wk.rank] + flag_words) + (gen & 1u) * T.P + L, gen);
-            // warp g takes the peers g, g + 8, ...: its first lane waits for the peer's flag, then the warp reads the
-            // peer's row -- the peers are read side by side, one NVLink round trip for all of them
+            // ---- sum over ranks through peer memory, PUSH + flag-in-data ("LL") protocol: this rank stores its row
+            // straight into every peer's buffer; each 64-bit sum travels as (low word, generation, high word,
+            // generation) -- two self-validating 8-byte halves -- so there is no fence and no separate flag, the
+            // transfer is one one-way NVLink trip, and every rank polls its OWN memory for the peers' rows.
+            // Buffer of rank p: [2 parities][n_ranks sources][2][P][A] elements of 16 bytes.  A slot written for
+            // generation g was last read for g - 2, which its reader finished before it published g - 1 (which this
+            // rank needed to get here), so the two parities never collide.
+            const size_t slot = ((size_t)(gen & 1u) * Wk.n_ranks) * 2 * n + off;
+            if (t < 2 * A) {
+                const unsigned long long v = s_row[t];
+                const uint4 pk = make_uint4((uint32_t)v, gen, (uint32_t)(v >> 32), gen);
+                for (int r = 0; r < Wk.n_ranks; ++r) {
+                    if (r == Wk.rank) continue;
+                    st_volatile_v4(reinterpret_cast<uint4*>(Wk.xchg[r]) + slot + (size_t)Wk.rank * 2 * n, pk);
+                }
+            }
+            trace_point(Wk, k, 7, true);          // rows pushed (latest row CTA)
+            // warp g takes the peers g, g + 8, ...: lane e polls element e of that peer's row in the local buffer
             unsigned long long from_peers = 0ull;
             for (int r = g; r < Wk.n_ranks; r += TABLE_THREADS / 32) {
                 if (r == Wk.rank) continue;
-                if (e == 0) {
-                    const unsigned int* flag = reinterpret_cast<const unsigned int*>(Wk.xchg[r] + flag_words) + (gen & 1u) * T.P + L;
+                if (e < 2 * A) {
+                    const uint4* src = reinterpret_cast<const uint4*>(Wk.xchg[Wk.rank]) + slot + (size_t)r * 2 * n;
+                    uint4 pk = ld_volatile_v4(src);
                     int spins = 0;
-                    while ((int)(ld_acquire_sys(flag) - gen) < 0) {
-                        // a peer is gone: do not hang the GPU, but never use its stale rows either -- raise the (sticky)
+                    while (pk.y != gen || pk.w != gen) {
+                        // a peer is gone: do not hang the GPU, but never use a stale row either -- raise the (sticky)
                         // flag the host checks at every synchronising call; this row's thresholds become zero below
-                        if (++spins > (1 << 22)) { atomicExch(&clk->xchg_error, 1); s_timeout = 1; break; }
-                        __nanosleep(64);
+                        if (++spins > (1 << 22)) { atomicExch(&clk->xchg_error, 1); s_timeout = 1; pk = make_uint4(0u, 0u, 0u, 0u); break; }
+                        __nanosleep(32);
+                        pk = ld_volatile_v4(src);
                     }
+                    from_peers += (unsigned long long)pk.x | ((unsigned long long)pk.z << 32);
                 }
-                __syncwarp();
-                if (e < 2 * A) from_peers += ld_relaxed_sys(Wk.xchg[r] + (size_t)(gen & 1u) * 2 * n + off);
             }
             s_part[g][e] = from_peers;
             __syncthreads();
+            trace_point(Wk, k, 9, true);          // every peer's row arrived (latest row CTA)
             if (t < 2 * A) {
                 unsigned long long total = s_row[t];
 #pragma unroll
