@@ -22,7 +22,7 @@ def load_reference(case):
 def build_world(root, ref):
     spec = synth.make_spec(n_districts=ref['n_districts'], R0=ref['R0'], seed=POP_SEED, start_datetime=datetime(2020, 9, 1, 0))
     pop = synth.make_population(ref['n_agents'], spec, seed=POP_SEED, scenario_flags=True)
-    if ref['case'] in ('selective_lockdown_100k', 'open_manufacturing_schools_100k'):
+    if ref['case'] in ('selective_lockdown_100k', 'open_manufacturing_schools_100k', 'open_manufacturing_schools_100k_120d'):
         # the census columns the sector / school scenarios read, exactly as tests/golden/make_ref_ensemble.py adds them
         names = np.array(synth.district_names(ref['n_districts']))
         pop.extras['manufacturing_workers'] = np.where(pop.extras['manufacturing_workers'] == 1, 1.0, np.nan)
