@@ -145,6 +145,7 @@ class Country:
     philox_seed = None            # None: drawn from numpy's global RNG at device creation (so np.random.seed pins a run)
     log_flush_days = 1            # write log lines every N simulated days (each flush synchronises with the GPU)
     max_days = 800
+    _sim_class = None             # tests substitute the engine (CPU double); None = abm_b200.engine.Simulation
 
     def __init__(self, params, model_log_file=None, individual_log_file=None):
         self.individual_log_file = individual_log_file       # accepted and never written, as in the reference
@@ -477,7 +478,7 @@ class Country:
             return self._sim
         if self.person_ids is None:
             raise RuntimeError('load_agents() has not been called')
-        from abm_b200 import tables
+        from abm_b200 import multi, tables
         from abm_b200.engine import Simulation
         n = self.person_ids.shape[0]
         # canonical order: (home district, household), ties in person order -- one stable sort of a combined key
@@ -514,10 +515,27 @@ class Country:
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
         pop.validate(spec)
+        # Under torchrun (one process per GPU, torch.distributed initialised) every rank has built the same host vectors
+        # from the same census and numpy seed; each keeps its household-aligned range of the canonical order on its GPU
+        # and `ShardedSimulation` makes the N stores look like one (abm_b200/multi.py).
+        n_ranks = multi.world_size()
+        if n_ranks > 1:
+            import os
+            device = int(os.environ.get('LOCAL_RANK', self.device_index))
+            seed = multi.broadcast_int(seed, device if self._sim_class is None else 'cpu')
+            if getattr(self, '_resumable', True) is False:
+                raise RuntimeError('this model was pickled from a multi-rank run without its device state: it can be read, not stepped')
         self._philox_seed = int(seed)
         self._spec_obj, self._pop = spec, pop
-        self._sim = Simulation(spec, pop, seed=self._philox_seed, device=self.device_index, tables=tables.build_tables(spec),
-                               max_days=self.max_days, upload=restore is None)
+        if n_ranks > 1:
+            self._sim = multi.ShardedSimulation(spec, pop, seed=self._philox_seed, device=device, tables=tables.build_tables(spec),
+                                                max_days=self.max_days, upload=restore is None, sim_class=self._sim_class)
+        else:
+            if getattr(self, '_resumable', True) is False:
+                raise RuntimeError('this model was pickled from a multi-rank run without its device state: it can be read, not stepped')
+            self._sim = (self._sim_class or Simulation)(spec, pop, seed=self._philox_seed, device=self.device_index,
+                                                        tables=tables.build_tables(spec), max_days=self.max_days,
+                                                        upload=restore is None)
         if restore is not None:
             self._sim.restore(restore)
             self._restore = None
@@ -679,11 +697,12 @@ class Country:
         if self._sim is None or self.model_log_file is None:
             self._log_rows_written = self._log_rows_due
             return
-        rows = self._sim.log_dicts()
-        for r in rows[self._log_rows_written:self._log_rows_due]:
-            data = dict(date=r['date'])
-            data.update({k: r[k] for k in _COUNTER_KEYS})
-            log_to_file(self.model_log_file, json.dumps(data), as_log=True, verbose=False)
+        rows = self._sim.log_dicts()             # multi-rank: summed over ranks (a collective: every rank calls it)
+        if getattr(self._sim, 'rank', 0) == 0:   # ... and rank 0 writes the file
+            for r in rows[self._log_rows_written:self._log_rows_due]:
+                data = dict(date=r['date'])
+                data.update({k: r[k] for k in _COUNTER_KEYS})
+                log_to_file(self.model_log_file, json.dumps(data), as_log=True, verbose=False)
         self._log_rows_written = max(self._log_rows_written, min(self._log_rows_due, len(rows)))
 
     # ------------------------------------------------------------------ pickling (scenario_models.py:497-500)
@@ -692,7 +711,11 @@ class Country:
         if self._sim is not None:
             if self.model_log_file is not None:
                 self.log_model_output()
-            d['_restore'] = self._sim.checkpoint()
+            try:
+                d['_restore'] = self._sim.checkpoint()
+            except NotImplementedError:                          # multi-rank: the gathered host vectors only
+                d['_restore'] = None
+                d['_resumable'] = False
             d['_log_rows_written'] = d['_log_rows_due'] = 0      # the day log restarts with the restored handle
             d['_host'] = {name: self._dynamic_vector(name) for name in _DYNAMIC}
         d['_sim'] = None

@@ -211,6 +211,10 @@ def run_scenario(scenarioClass, scenario_name, sim_fname, R0, sample_size, seed_
             break
 
     model_dump_file = get_data_dir('logs', f'model_dump_file_{sim_fname}.{now}.pickle')
-    with open(model_dump_file, 'wb') as fl:
-        pickle.dump(model, fl)
+    # several ranks (torchrun): gathering the vectors for the pickle is a collective, so every rank serialises the model;
+    # rank 0 writes the one file
+    payload = pickle.dumps(model)
+    if getattr(model._sim, 'rank', 0) == 0:
+        with open(model_dump_file, 'wb') as fl:
+            fl.write(payload)
     return model

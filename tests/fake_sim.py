@@ -16,9 +16,21 @@ from oracle.abm_oracle import OracleModel
 class FakeSimulation:
     instances = []
 
-    def __init__(self, spec, pop, seed=0, device=0, tables=None, max_days=400, upload=True, **kw):
+    def __init__(self, spec, pop, seed=0, device=0, tables=None, max_days=400, upload=True, agent_id_base=0, world_size=1,
+                 rank=0, **kw):
         self.spec, self.pop, self.tab, self.seed = spec, pop, tables, seed
-        self.ora = OracleModel(pop, dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob), tables, seed)
+        self.agent_id_base = int(agent_id_base)
+        reduce_fn = None
+        if world_size > 1:            # a shard: the district x status tables are summed over the (gloo) ranks
+            import torch
+            import torch.distributed as dist
+
+            def reduce_fn(buf):
+                t = torch.from_numpy(buf.view(np.int64).copy())
+                dist.all_reduce(t)
+                return t.numpy().view(np.uint64)
+        self.ora = OracleModel(pop, dict(od_cum=spec.od_cum, mild_prob=spec.mild_symptom_move_prob), tables, seed,
+                               agent_id_base=agent_id_base, reduce_fn=reduce_fn)
         self.n_refresh = 0
         self.log_base = 0
         FakeSimulation.instances.append(self)
@@ -28,7 +40,7 @@ class FakeSimulation:
         return self.ora.k
 
     def seed_infections(self, ids):
-        self.ora.set_epidemic_status(np.asarray(ids, dtype=np.int64))
+        self.ora.set_epidemic_status(np.asarray(ids, dtype=np.int64) - self.agent_id_base)      # global -> local ids
 
     def step(self, n=1):
         for _ in range(int(n)):
@@ -66,11 +78,20 @@ class FakeSimulation:
                 st[key] = loc
         return st
 
-    def log_dicts(self):
+    def read_log(self):
+        rows = np.zeros((len(self.ora.log_rows) - self.log_base, 16), dtype=np.int64)
+        for i, r in enumerate(self.ora.log_rows[self.log_base:]):
+            rows[i, :12] = [r[k] for k in COUNTER_NAMES]
+            rows[i, 12] = r['tick']
+        return rows
+
+    def log_dicts(self, rows=None):
+        rows = self.read_log() if rows is None else rows
         out = []
-        for r in self.ora.log_rows[self.log_base:]:
-            d = dict(r)
-            d['date'] = (self.spec.start_datetime + timedelta(minutes=int(r['tick']))).isoformat()
+        for r in rows:
+            d = {name: int(r[i]) for i, name in enumerate(COUNTER_NAMES)}
+            d['tick'] = int(r[12])
+            d['date'] = (self.spec.start_datetime + timedelta(minutes=int(r[12]))).isoformat()
             out.append(d)
         return out
 
