@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument('--cpu-agents', type=int, default=1_500_000, help='agents of the bounded CPU sample (numpy port)')
     ap.add_argument('--ref-agents', type=int, default=100_000, help='agents per replica of the real reference (baseline/_ref)')
     ap.add_argument('--ref-procs', type=int, default=0, help='replicas of the reference arm (0 = one per host core, at most 32)')
+    ap.add_argument('--no-ingest', action='store_true', help='skip the timed device-side ingestion leg')
     ap.add_argument('--no-parity-check', action='store_true', help='skip the sharding-invariance check before the timed region')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -297,6 +298,34 @@ def run_cuda_arm(a):
                 print('bench: sharding parity check FAILED: ' + json.dumps(parity), file=sys.stderr, flush=True)
             sys.exit(1)
 
+    # ---- ingestion: this rank's agents as integer columns in shuffled PERSON order (what load_agents has
+    #      after resolving names) -> canonical sort, sub-tile packing, bit packing on the device -> first sub-step
+    ingest = None
+    if agent_ids is None and not a.no_ingest:
+        from abm_b200.ingest import DeviceStore
+        perm = np.random.default_rng(POP_SEED + rank).permutation(pop.n)
+        cols = {name: np.ascontiguousarray(getattr(pop, name)[perm]) for name in
+                ('district', 'household', 'age', 'status', 'econ_kind', 'district_mover', 'move_prob_weekday', 'move_prob_other')}
+        barrier()
+        t0 = time.perf_counter()
+        dstore = DeviceStore(spec, device=local, agent_id_base=base, **cols)
+        t_store = time.perf_counter() - t0
+        isim = Simulation(spec, dstore.pop, seed=POP_SEED, device=local, tables=tab, max_days=4, agent_id_base=base,
+                          district_start=dstart, world_size=1, host_store=dstore)
+        isim.step(1)
+        isim.sync()
+        t_first = time.perf_counter() - t0
+        same = all(torch.equal(dstore.host[k].cpu(), store.host[k]) for k in store.host)
+        isim.close()
+        del isim, dstore, cols, perm
+        torch.cuda.empty_cache()
+        ingest = dict(ingest_s=t_first, store_built_s=t_store, agents=pop.n, equals_host_store=bool(same),
+                      what='integer census columns in shuffled person order (host numpy) -> upload, device sort by (district, '
+                           'household), sub-tile packing, bit packing -> Simulation -> first sub-step executed; per rank')
+        if not same:
+            print('bench: device-built store differs from the host-built one', file=sys.stderr, flush=True)
+            sys.exit(1)
+
     sim = make_sim()
     sim.seed_infections(local_seeds)
     sim.step(a.spinup * SUBSTEPS_PER_DAY)
@@ -469,6 +498,7 @@ def run_cuda_arm(a):
                                       f'seeded with {a.seed_fraction:.2%} of the agents (state_at_timing = where they end); '
                                       'worst_timed_day_ms is the most expensive of them, full_run.worst_day the most expensive day '
                                       'of the whole scenario',
+                        ingest=ingest, ingest_s=None if ingest is None else ingest['ingest_s'],
                         worst_timed_day_ms=worst_timed_day_ms, timed_day_ms=[round(v, 4) for v in day_ms],
                         full_run=full_run),
             roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks.summary(),

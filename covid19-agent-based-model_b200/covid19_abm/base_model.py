@@ -133,6 +133,92 @@ class EpidemicScheduler:
         return rates
 
 
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+class _IdNameTable(dict):
+    """`{id: name}` (or, inverted, `{name: id}`) of millions of consecutive ids, as the plain dict the reference keeps
+    (base_model.py:577-611), but filled on first use: building 3.7 M-entry dictionaries costs seconds at load time and
+    nothing in the step reads them.  A real dict subclass, so every dict operation works once it is filled."""
+
+    _pending = None
+
+    def __init__(self, names, first_id, inverted=False, extra=()):
+        super().__init__()
+        self._pending = (names, int(first_id), bool(inverted), tuple(extra))
+
+    def __reduce__(self):                       # pickles (and deep-copies) as the plain dict it stands for
+        return (dict, (dict(self._fill()),))
+
+    def _fill(self):
+        if self._pending is not None:
+            (names, first, inverted, extra), self._pending = self._pending, None
+            for e in extra:                      # earlier tables first: later entries win, like dict.update
+                dict.update(self, e)
+            seq = names.tolist() if hasattr(names, 'tolist') else list(names)
+            dict.update(self, zip(seq, range(first, first + len(seq))) if inverted else enumerate(seq, first))
+        return self
+
+    def last_id(self):
+        """max(keys) of an id -> name table without filling it."""
+        if self._pending is not None and not self._pending[2] and not self._pending[3]:
+            return self._pending[1] + len(self._pending[0]) - 1
+        return max(self._fill().keys())
+
+
+def _forward(name):
+    def method(self, *a, **kw):
+        return getattr(dict, name)(self._fill(), *a, **kw)
+    method.__name__ = name
+    return method
+
+
+for _n in ('__getitem__', '__iter__', '__len__', '__contains__', '__eq__', '__repr__', 'get', 'items', 'keys', 'values',
+           '__setitem__', '__delitem__', 'update', 'pop', 'copy', '__or__', '__ror__', 'setdefault'):
+    setattr(_IdNameTable, _n, _forward(_n))
+
+
+class _InvertedLocations(_IdNameTable):
+    """`{location name: id}` = inversion of districts + households (+ schools) merged in that order."""
+
+    def __init__(self, district_id_to_name, hh_names, first_household, schools):
+        dict.__init__(self)
+        self._pending = (district_id_to_name, hh_names, int(first_household), schools)
+
+    def _fill(self):
+        if self._pending is not None:
+            (districts, hh_names, first, schools), self._pending = self._pending, None
+            dict.update(self, {n: i for i, n in districts.items()})
+            seq = hh_names.tolist() if hasattr(hh_names, 'tolist') else list(hh_names)
+            dict.update(self, zip(seq, range(first, first + len(seq))))
+            for sc in schools:
+                dict.update(self, {n: i for i, n in sc.items()})
+        return self
+
+    def last_id(self):
+        return max(self._fill().values())
+
+
+def _last_id(table):
+    return table.last_id() if isinstance(table, _IdNameTable) else max(table)
+
+
+class _Never:
+    """Stand-in for `np.full(size, datetime.max)` (object dtype: 8 bytes and a reference count per element) until
+    somebody reads the vector before the device store exists."""
+
+    def __init__(self, size, value):
+        self.size, self.value = size, value
+
+    def make(self):
+        return np.full(shape=self.size, fill_value=self.value)
+
+
 class Country:
     STATE_SUSCEPTIBLE, STATE_INFECTED, STATE_CONTAGIOUS, STATE_RECOVERED, STATE_DEAD = 0, 1, 2, 3, 4
     DEAD_LOCATION_ID = -1
@@ -146,6 +232,7 @@ class Country:
     log_flush_days = 1            # write log lines every N simulated days (each flush synchronises with the GPU)
     max_days = 800
     _sim_class = None             # tests substitute the engine (CPU double); None = abm_b200.engine.Simulation
+    ingest_on_device = True       # build the packed agent store on the GPU (abm_b200/ingest.py) instead of in numpy
 
     def __init__(self, params, model_log_file=None, individual_log_file=None):
         self.individual_log_file = individual_log_file       # accepted and never written, as in the reference
@@ -186,7 +273,7 @@ class Country:
         h['infected_symptomatic_status'] = np.full(shape=size, fill_value=self.SYMPTOM_NONE)
         h['clinical_state'] = np.full(shape=size, fill_value=self.CLINICAL_NOT_HOSPITALIZED)
         for name in ('date_infected', 'date_start_contagious', 'date_start_symptomatic', 'date_recovered'):
-            h[name] = np.full(shape=size, fill_value=datetime.max)
+            h[name] = _Never(size, datetime.max)
         h['infected_at_district_ids'] = np.full(shape=size, fill_value=-1)
         h['infected_at_location_ids'] = np.full(shape=size, fill_value=-1)
         self.severe_disease_risk = np.ones(shape=size)        # quirk Q2: whatever the scenario hook stored is overwritten
@@ -194,7 +281,7 @@ class Country:
     def initialize_clinical_vectors(self, size):
         for name in ('date_start_hospitalized', 'date_end_hospitalized', 'date_start_critical', 'date_end_critical',
                      'date_died'):
-            self._host[name] = np.full(shape=size, fill_value=datetime.max)
+            self._host[name] = _Never(size, datetime.max)
 
     def initialize_agent_vectors(self, df):
         p = self.params
@@ -204,20 +291,20 @@ class Country:
         # base_model.py:577-611, are what dominates its load time at millions of agents)
         hh_codes, hh_names = pd.factorize(df['household_id'].astype(str), sort=True)
         hh_names = np.asarray(hh_names)
-        p.HOUSEHOLD_ID_TO_NAME = dict(enumerate(hh_names.tolist(), first_household))
-        p.HOUSEHOLD_NAME_TO_ID = {n: i for i, n in p.HOUSEHOLD_ID_TO_NAME.items()}
+        p.HOUSEHOLD_ID_TO_NAME = _IdNameTable(hh_names, first_household)
+        p.HOUSEHOLD_NAME_TO_ID = _IdNameTable(hh_names, first_household, inverted=True)
         if self.is_school_scenario:                             # schools after the households
-            first_school = max(p.HOUSEHOLD_ID_TO_NAME) + 1
+            first_school = _last_id(p.HOUSEHOLD_ID_TO_NAME) + 1
             school_names = sorted(df.loc[df['school_id'] != '', 'school_id'].unique())
             p.SCHOOL_ID_TO_NAME = dict(enumerate(school_names, first_school))
             p.SCHOOL_NAME_TO_ID = {n: i for i, n in p.SCHOOL_ID_TO_NAME.items()}
         p.SEX_ID_TO_NAME = dict(enumerate(sorted(df['sex'].unique())))
         p.SEX_NAME_TO_ID = {n: i for i, n in p.SEX_ID_TO_NAME.items()}
-        p.LOCATION_ID_TO_NAME = dict(p.DISTRICT_ID_TO_NAME)
-        p.LOCATION_ID_TO_NAME.update(p.HOUSEHOLD_ID_TO_NAME)
-        if self.is_school_scenario:
-            p.LOCATION_ID_TO_NAME.update(p.SCHOOL_ID_TO_NAME)
-        p.LOCATION_NAME_TO_ID = {n: i for i, n in p.LOCATION_ID_TO_NAME.items()}
+        schools = (p.SCHOOL_ID_TO_NAME,) if self.is_school_scenario else ()
+        p.LOCATION_ID_TO_NAME = _IdNameTable(hh_names, first_household, extra=(p.DISTRICT_ID_TO_NAME,) + schools)
+        # (inverted: districts, then households, then schools -- a name that is both a district and a household resolves
+        # to the household, a school name to the school, exactly like inverting the merged id -> name dict)
+        p.LOCATION_NAME_TO_ID = _InvertedLocations(p.DISTRICT_ID_TO_NAME, hh_names, first_household, schools)
 
         def codes_of(column, names_by_id):
             """ids of a string column whose names are those of `names_by_id` (id -> name): the column is hashed once
@@ -253,7 +340,8 @@ class Country:
         loc = np.where(own_household, self.household_ids, np.where(own_district, self.district_ids, -1)).astype(np.int64)
         # a name that is both a district and a household (mining camps) resolves to the household, as in the inverted
         # dictionary of the reference (base_model.py:594-599)
-        both = set(p.DISTRICT_NAME_TO_ID).intersection(p.HOUSEHOLD_NAME_TO_ID)
+        hh_name_set = pd.Index(hh_names)
+        both = {n for n in p.DISTRICT_NAME_TO_ID if n in hh_name_set}
         rest = loc < 0
         if both:
             rest |= own_district & pd.Series(place).isin(both).values
@@ -435,7 +523,7 @@ class Country:
         school_district = None
         if n_schools:
             # a school's hand-washing multiplier is that of the district most of its pupils live in
-            first_school = max(p.HOUSEHOLD_ID_TO_NAME) + 1
+            first_school = _last_id(p.HOUSEHOLD_ID_TO_NAME) + 1
             sid = self.school_ids - first_school
             ok = ~np.isnan(sid.astype(np.float64)) & (sid >= 0)
             school_district = np.zeros(n_schools, dtype=np.int32)
@@ -460,7 +548,7 @@ class Country:
         kind[loc == hh] = C.EKIND_HOUSEHOLD
         pool = np.zeros(loc.shape[0], dtype=np.int32)
         if self.is_school_scenario:
-            first_school = max(self.params.HOUSEHOLD_ID_TO_NAME) + 1
+            first_school = _last_id(self.params.HOUSEHOLD_ID_TO_NAME) + 1
             at_school = loc >= first_school
             kind[at_school] = C.EKIND_POOL
             pool[at_school] = D + (loc[at_school] - first_school)
@@ -481,36 +569,50 @@ class Country:
         from abm_b200 import multi, tables
         from abm_b200.engine import Simulation
         n = self.person_ids.shape[0]
-        # canonical order: (home district, household), ties in person order -- one stable sort of a combined key
-        span = int(self.household_ids.max()) + 1
-        if int(self.district_ids.max()) < (2 ** 62) // span:
-            order = np.argsort(self.district_ids.astype(np.int64) * span + self.household_ids, kind='stable')
+        if self.age.min() < 0 or self.age.max() > 99:
+            raise ValueError('ages must lie in 0..99 (params.ages)')
+        n_ranks = multi.world_size()
+        store = None
+        if self._sim_class is None and n_ranks == 1 and self._restore is None and self.ingest_on_device and _cuda_available():
+            # the store is built where it is going to live: the integer columns go up in person order; sort, gather,
+            # sub-tile packing and bit packing run on the device (abm_b200/ingest.py); the canonical-order columns come back
+            from abm_b200.ingest import DeviceStore
+            kind_p, pool_p = self._econ_encoding(np.arange(n))
+            store = DeviceStore(self._spec(), district=self.district_ids, household=self.household_ids, age=self.age,
+                                status=self.economic_status_ids, econ_kind=kind_p, district_mover=self.district_mover,
+                                move_prob_weekday=self.economic_status_weekday_movement_probability,
+                                move_prob_other=self.economic_status_other_day_movement_probability, econ_pool=pool_p,
+                                device=self.device_index)
+            order, pop = store.order, store.pop
         else:
-            order = np.lexsort((self.household_ids, self.district_ids))
-        hh = self.household_ids[order]
-        new_hh = np.r_[True, hh[1:] != hh[:-1]]
-        dense = np.cumsum(new_hh) - 1
-        lowest = int(self.household_ids.min())
-        if int(dense[-1]) + 1 != int(np.count_nonzero(np.bincount(self.household_ids - lowest))):
-            raise NotImplementedError('a household has members with different home districts: the household-aligned device '
-                                      'layout cannot hold it')
+            # canonical order: (home district, household), ties in person order -- one stable sort of a combined key
+            span = int(self.household_ids.max()) + 1
+            if int(self.district_ids.max()) < (2 ** 62) // span:
+                order = np.argsort(self.district_ids.astype(np.int64) * span + self.household_ids, kind='stable')
+            else:
+                order = np.lexsort((self.household_ids, self.district_ids))
+            hh = self.household_ids[order]
+            new_hh = np.r_[True, hh[1:] != hh[:-1]]
+            dense = np.cumsum(new_hh) - 1
+            lowest = int(self.household_ids.min())
+            if int(dense[-1]) + 1 != int(np.count_nonzero(np.bincount(self.household_ids - lowest))):
+                raise NotImplementedError('a household has members with different home districts: the household-aligned device '
+                                          'layout cannot hold it')
+            kind, pool = self._econ_encoding(order)
+            pop = Population(
+                district=self.district_ids[order].astype(np.int32), household=dense.astype(np.int64),
+                age=self.age[order].astype(np.int32), status=self.economic_status_ids[order].astype(np.int32), econ_kind=kind,
+                district_mover=self.district_mover[order].astype(np.int8),
+                move_prob_weekday=self.economic_status_weekday_movement_probability[order].astype(np.float64),
+                move_prob_other=self.economic_status_other_day_movement_probability[order].astype(np.float64), econ_pool=pool)
         self._order = order
         self._canon_of_person = np.empty(n, dtype=np.int64)
         self._canon_of_person[order] = np.arange(n)
-        kind, pool = self._econ_encoding(order)
-        if self.age.min() < 0 or self.age.max() > 99:
-            raise ValueError('ages must lie in 0..99 (params.ages)')
-        pop = Population(
-            district=self.district_ids[order].astype(np.int32), household=dense.astype(np.int64),
-            age=self.age[order].astype(np.int32), status=self.economic_status_ids[order].astype(np.int32), econ_kind=kind,
-            district_mover=self.district_mover[order].astype(np.int8),
-            move_prob_weekday=self.economic_status_weekday_movement_probability[order].astype(np.float64),
-            move_prob_other=self.economic_status_other_day_movement_probability[order].astype(np.float64), econ_pool=pool)
         restore = self._restore
         if restore is not None:                               # unpickled model: same clock origin, same draw key
             spec, seed = self._spec_obj, self._philox_seed
         else:
-            spec = self._spec()
+            spec = store.spec if store is not None else self._spec()
             seed = self.philox_seed
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
@@ -518,7 +620,6 @@ class Country:
         # Under torchrun (one process per GPU, torch.distributed initialised) every rank has built the same host vectors
         # from the same census and numpy seed; each keeps its household-aligned range of the canonical order on its GPU
         # and `ShardedSimulation` makes the N stores look like one (abm_b200/multi.py).
-        n_ranks = multi.world_size()
         if n_ranks > 1:
             import os
             device = int(os.environ.get('LOCAL_RANK', self.device_index))
@@ -533,9 +634,10 @@ class Country:
         else:
             if getattr(self, '_resumable', True) is False:
                 raise RuntimeError('this model was pickled from a multi-rank run without its device state: it can be read, not stepped')
+            kw = dict(host_store=store) if store is not None else {}
             self._sim = (self._sim_class or Simulation)(spec, pop, seed=self._philox_seed, device=self.device_index,
                                                         tables=tables.build_tables(spec), max_days=self.max_days,
-                                                        upload=restore is None)
+                                                        upload=restore is None, **kw)
         if restore is not None:
             self._sim.restore(restore)
             self._restore = None
@@ -598,7 +700,10 @@ class Country:
 
     def _dynamic_vector(self, name):
         if self._sim is None:
-            return self._host[name]
+            v = self._host[name]
+            if isinstance(v, _Never):
+                v = self._host[name] = v.make()
+            return v
         if name not in self._fresh:
             if 'epidemic_state' not in self._fresh:
                 self._read_back()

@@ -4,7 +4,7 @@
 tag=${1:-x}
 timeout 900 python -m pytest tests -m gpu -x -q -k "not ensemble" > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$tag.log
 tail -4 gpurun_out/pytest_$tag.log
-timeout 600 python bench.py --no-cpu-baseline --no-e2e --full-run-days 0 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -2 gpurun_out/bench_$tag.err
+timeout 600 python bench.py --no-cpu-baseline --no-e2e --no-ingest --full-run-days 0 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -2 gpurun_out/bench_$tag.err
 python - <<PY
 import json
 try:
