@@ -303,7 +303,9 @@ def run_cuda_arm(a):
     ingest = None
     if agent_ids is None and not a.no_ingest:
         from abm_b200.ingest import DeviceStore
-        perm = np.random.default_rng(POP_SEED + rank).permutation(pop.n)
+        # households in random order (members of a household keep their census order, which the stable canonical sort
+        # preserves, so the device-built store can be compared word for word with the host-built one)
+        perm = np.argsort(np.random.default_rng(POP_SEED + rank).permutation(pop.n_households)[pop.household], kind='stable')
         cols = {name: np.ascontiguousarray(getattr(pop, name)[perm]) for name in
                 ('district', 'household', 'age', 'status', 'econ_kind', 'district_mover', 'move_prob_weekday', 'move_prob_other')}
         barrier()
@@ -320,7 +322,7 @@ def run_cuda_arm(a):
         del isim, dstore, cols, perm
         torch.cuda.empty_cache()
         ingest = dict(ingest_s=t_first, store_built_s=t_store, agents=pop.n, equals_host_store=bool(same),
-                      what='integer census columns in shuffled person order (host numpy) -> upload, device sort by (district, '
+                      what='integer census columns with the households in random order (host numpy) -> upload, device sort by (district, '
                            'household), sub-tile packing, bit packing -> Simulation -> first sub-step executed; per rank')
         if not same:
             print('bench: device-built store differs from the host-built one', file=sys.stderr, flush=True)
