@@ -17,8 +17,9 @@ ap.add_argument('--agents', type=int, default=15_000_000)
 ap.add_argument('--spinup', type=int, default=40)
 ap.add_argument('--days', type=int, default=2)
 ap.add_argument('--seed-fraction', type=float, default=0.002)
+ap.add_argument('--districts', type=int, default=60)
 a = ap.parse_args()
-spec = synth.make_spec(n_districts=60, R0=1.9, seed=2020)
+spec = synth.make_spec(n_districts=a.districts, R0=1.9, seed=2020)
 pop = synth.make_population(a.agents, spec, seed=2020)
 seeds = synth.pick_seeds(pop, spec, infect_num=max(1, int(a.seed_fraction * pop.n)), seed=2020)
 sim = Simulation(spec, pop, seed=2020, tables=tables.build_tables(spec), max_days=a.spinup + a.days + 4)
