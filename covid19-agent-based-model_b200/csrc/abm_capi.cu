@@ -2,9 +2,10 @@
 //
 // Replaces, for the hot path only, what Country / EpidemicScheduler do on the host in the reference
 // (/root/reference/src/covid19_abm/base_model.py:20-441, 838-1106): owns the constant tables, the
-// district x status accumulators, the day log, the sub-step clock, and launches the kernels of
-// abm_kernels.cuh on one CUDA stream.  Multi-GPU: one handle per rank, the accumulators are summed over
-// ranks with one ncclAllReduce per sub-step (NCCL is loaded with dlopen so a single-GPU build has no
+// district x status accumulators, the event queues, the day log, the sub-step clock, and launches the kernels of
+// abm_kernels.cuh (sweep, event kernel, table kernel per sub-step; whole days as CUDA graphs) on one CUDA stream.
+// Multi-GPU: one handle per rank; the accumulators are summed over ranks inside the table kernel through peer memory
+// (one node), or with one ncclAllReduce per sub-step (NCCL is loaded with dlopen so a single-GPU build has no
 // link-time dependency on it).
 #include <cuda_runtime.h>
 #include <dlfcn.h>

@@ -1,6 +1,6 @@
 // abm_kernels.cuh -- sm_100a kernels of the covid19_abm agent step.
 //
-// One launch of abm_substep_kernel per 4-hour sub-step does, for every agent slot, in this order:
+// One 4-hour sub-step does, for every agent, in this order:
 //   I(k-1)  infection draw of the previous sub-step against the district x status threshold table and the
 //           household hazard (reference: EpidemicScheduler.step location loop, base_model.py:60-175, in
 //           its pressure-table form) and, on infection, the whole disease course
@@ -9,27 +9,27 @@
 //           contagious promotion (base_model.py:54-58)
 //   M(k)    go_home at hour 16 / go_out + OD mobility at hour 8 (base_model.py:274-441)
 //   A(k)    accumulation of the district x status infectious-pressure and headcount tables
-// Fusing I(k-1) into the launch of sub-step k means the 8-byte hot record of an agent is read once
-// per sub-step.  abm_hazard_table_kernel then turns the accumulated tables into 31-bit Bernoulli
-// thresholds for the next launch and keeps the day log (Country.log_model_output, base_model.py:1082-1106).
+// Fusing I(k-1) into the launch of sub-step k means the 8-byte hot record of an agent is read once per sub-step.
+// The work is split by KIND OF CONTROL FLOW over three launches:
+//   abm_sweep_kernel         every slot, the dense per-agent work; agents that need a rare code path are deferred
+//   abm_event_kernel         one thread per deferred agent: infection events, due transitions, departures
+//   abm_hazard_table_kernel  accumulated tables -> 31-bit Bernoulli thresholds for the next launch, the sum over ranks,
+//                            the day log (Country.log_model_output, base_model.py:1082-1106), the clock
 //
-// Execution model: ONE WARP OWNS ONE SUB-TILE of 128 consecutive agent slots (lane l holds slots
+// Sweep execution model: ONE WARP OWNS ONE SUB-TILE of 128 consecutive agent slots (lane l holds slots
 // 4l..4l+3, one 128-bit load per hot word).  The host layout guarantees that a sub-tile holds whole
 // households of a single home district and that slot offset o of a sub-tile is canonical agent id
 // base + o with base a multiple of 4, so (a) the household hazard is a warp-local segmented sum,
 // (b) the home district is a per-warp scalar and (c) one Philox4x32 block serves the four agents of a
-// lane.  Warps never wait for each other: every warp keeps its own event tallies and accumulator row and flushes them itself.
-// The kernel is instruction-issue bound, not HBM bound (profiles/), so the code below is organised to
-// issue few instructions: flag fields that are tested together are adjacent, work that only a few agents
-// need (disease-course sampling, due transitions, travellers) runs in "funnel" loops -- every lane keeps
-// a bit mask of its agents that need it and the warp iterates until all masks are empty, so the cost
-// is max-per-lane, not four passes -- and the hazard -> probability map is integer arithmetic.
+// lane.  Warps never wait for each other.  The sweep is instruction-issue bound, not HBM bound (profiles/), so it is
+// organised to issue few instructions: flag fields that are tested together are adjacent, the four agents of a lane run
+// through predicated straight-line code, and the hazard -> probability map is integer arithmetic.
 //
 // All random numbers are Philox4x32-10 keyed by the seed.  Counter = (id, id >> 32, sub-step, site):
 // id = agent_id >> 2 for the group sites (word agent_id & 3 belongs to the agent), id = agent_id for
 // the disease-course sites.  Everything that is compared against the oracle is integer arithmetic or
 // IEEE double +,*,/ through the __d*_rn intrinsics (never contracted to FMA), so results are
-// bit-identical to oracle/abm_oracle.py.
+// bit-identical to oracle/abm_oracle.py -- whichever kernel handles an agent.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
