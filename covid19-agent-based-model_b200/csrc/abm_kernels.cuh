@@ -607,7 +607,7 @@ constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mo
                 const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));                \
                 const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                \
                 *dst-- = make_uint4(slot0 + j, fj, aj, EV_LEAVER | (word_of(XO, (int)j) >> 1));      \
-                prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS);                     \
+                if ((fj & F_EPI_MASK) != EPI_S) prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS); \
                 prefetch_l2_keep(G.flags + slot0 + j);                                               \
                 prefetch_l2_keep(G.aux + slot0 + j);                                                 \
             } while (m);                                                                             \
@@ -641,15 +641,6 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
     const uint32_t slot0 = sub * SUB + lane * PER_LANE;
     const uint32_t A = (uint32_t)T.A;
 
-#ifdef ABM_PF_DIST
-    // L2 prefetch of the hot words of the tile ABM_PF_DIST CTAs ahead (one 128-byte line per 8 lanes)
-    if ((lane & 7) == 0 && (cta + ABM_PF_DIST) * WARPS < Wk.n_sub) {
-        const uint32_t pslot = slot0 + ABM_PF_DIST * WARPS * SUB;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(G.flags + pslot));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(G.aux + pslot));
-        if (lane == 0 && (mode_static & M_INFECT)) asm volatile("prefetch.global.L2 [%0];" ::"l"(G.hh_index + (pslot >> 2)));
-    }
-#endif
     // streaming loads / stores (evict-first): the hot words are touched once per launch and must not push the small
     // tables every warp re-reads out of L1
     const uint4 f4 = __ldcs(reinterpret_cast<const uint4*>(G.flags + slot0));
@@ -1023,7 +1014,17 @@ abm_event_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
                 const uint32_t dest = od_destination(od_row, T.D, e.w & 0x7FFFFFFFu);
                 if (dest != (uint32_t)L0) {                                             // :410-439
                     const uint32_t xs = word_of(group_draws(T, cid, s.k, SITE_STAY), J);
-                    G.cold[(size_t)slot * ABM_COLD_WORDS + ABM_COLD_T_RETURN] = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
+                    const int32_t t_ret = stay_return_tick(T, xs, s.weekday, (uint32_t)L0, dest, s.now);
+                    if ((f & F_EPI_MASK) == EPI_S) {
+                        // never infected: the rest of the cold record is known (dates = never, inf_at = 0), so the whole
+                        // 32-byte sector is overwritten -- a scattered 4-byte store into a sector that is not in L2 costs a
+                        // DRAM read-modify-write, and a million of those at 08:00 were half of this kernel's time
+                        int4* p = reinterpret_cast<int4*>(G.cold) + (size_t)slot * 2;
+                        p[0] = make_int4(T_NEVER, T_NEVER, T_NEVER, T_NEVER);
+                        p[1] = make_int4(t_ret, 0, 0, 0);
+                    } else {
+                        G.cold[(size_t)slot * ABM_COLD_WORDS + ABM_COLD_T_RETURN] = t_ret;
+                    }
                     f = set_loc(f, LOC_DEST) | F_AWAY;
                     a = (a & 0xFFFF0000u) | dest;
                 } else {
