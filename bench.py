@@ -53,8 +53,10 @@ def parse_args():
     ap.add_argument('--no-parity-check', action='store_true', help='skip the sharding-invariance check before the timed region')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--shards', default='contiguous', choices=['contiguous', 'dealt'],
-                    help='multi-GPU sharding: contiguous ranges of the canonical order, or one piece of every district per rank')
+    ap.add_argument('--shards', default='dealt', choices=['contiguous', 'dealt'],
+                    help='multi-GPU sharding: one piece of every district per rank (default: the ranks are statistically alike, '
+                         'no rank is the slowest of every sub-step -- 125.6 vs 131.4 us per sub-step at N = 8, '
+                         'profiles/r02_timeline_8gpu_{dealt,contiguous}.txt), or contiguous ranges of the canonical order')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: sum the tables over ranks inside the table kernel through peer memory, or with ncclAllReduce')
     ap.add_argument('--full-run-days', type=int, default=365, help='also time a whole run of this many days from the seeding (0 = skip)')
