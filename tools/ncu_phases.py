@@ -60,9 +60,12 @@ for r in rows[hdr[0] + 1:end]:
         line = int(r[0])
     except ValueError:
         continue
-    n = float(r[col['Instructions Executed']] or 0)
-    s = float(r[col['# Samples']] or 0)
-    t = float(r[col['Thread Instructions Executed']] or 0) if 'Thread Instructions Executed' in col else 0.0
+    try:
+        n = float(r[col['Instructions Executed']] or 0)
+        s = float(r[col['# Samples']] or 0)
+        t = float(r[col['Thread Instructions Executed']] or 0) if 'Thread Instructions Executed' in col else 0.0
+    except ValueError:            # a source line with commas inside a string literal (inline asm): skip it
+        continue
     g = phase_of(line)
     ins[g] += n; smp[g] += s; thr[g] += t; ti += n; ts += s
 for name in sorted(ins, key=lambda k: -ins[k]):
