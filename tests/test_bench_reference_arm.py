@@ -1,7 +1,10 @@
 """bench.py's CPU arm machinery, without a GPU: the unmodified reference (baseline/_ref, installed by
 `__graft_entry__.build()` wherever the reference checkout exists) steps through `baseline/ref_harness.py`, and the numpy
 port leg runs.  Tiny populations: this checks plumbing, not speed."""
+import hashlib
+import json
 import os
+import subprocess
 import sys
 
 import pytest
@@ -21,12 +24,15 @@ def test_unmodified_reference_replica_runs():
     import bench
     if not bench._reference_available():
         pytest.skip('baseline/_ref not installed here (needs the reference checkout: python baseline/make_ref.py)')
-    secs, t_load, prev = bench._ref_replica((4_000, 12, 0.02, 2, 0, 1, 0))
+    # in a child process, as bench.py runs it: the harness puts the reference's own `covid19_abm` package on sys.path,
+    # which must not shadow the drop-in package of the same name for the tests that follow
+    code = ('import json, sys; sys.path.insert(0, %r); import bench; '
+            'print(json.dumps(bench._ref_replica((4_000, 12, 0.02, 2, 0, 1, 0))))' % ROOT)
+    out = subprocess.run([sys.executable, '-c', code], check=True, capture_output=True, text=True, cwd=ROOT).stdout
+    secs, t_load, prev = json.loads(out.strip().splitlines()[-1])
     assert secs > 0 and t_load > 0
     assert prev['agents'] == 4_000 and prev['ever_infected'] >= 80          # at least the seeds (int(p * n) + 1 per district)
     # the sources it ran are the unmodified reference's: same bytes as the manifest says
-    import hashlib
-    import json
     man = json.load(open(os.path.join(ROOT, 'baseline', '_ref', 'MANIFEST.json')))
     for rel, digest in man['files'].items():
         if rel == 'MANIFEST.json':
