@@ -205,7 +205,12 @@ int launch_main(abm_handle* h, uint32_t mode) {
     const bool pdl = h->cfg.use_pdl != 0;
     const dim3 grid((unsigned)n_ctas);
     // the sub-step kinds of a simulated day get their own instantiation; anything else is generic
-#define ABM_LAUNCH(MODE) CUDA_TRY(h, launch_pdl(abm_sweep_kernel<MODE>, grid, block, h->stream, pdl, h->T, h->G, w, (const DevClock*)h->clock, m))
+    // (the instantiation with the timeline stamps only while a trace buffer is attached: abm_set_trace)
+#define ABM_LAUNCH(MODE)                                                                                                          \
+    do {                                                                                                                          \
+        if (h->trace) CUDA_TRY(h, launch_pdl(abm_sweep_kernel<MODE, true>, grid, block, h->stream, pdl, h->T, h->G, w, (const DevClock*)h->clock, m));  \
+        else CUDA_TRY(h, launch_pdl(abm_sweep_kernel<MODE, false>, grid, block, h->stream, pdl, h->T, h->G, w, (const DevClock*)h->clock, m)); \
+    } while (0)
     if (m == (M_INFECT | M_STEP | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_INCR);                       // night
     else if (m == (M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR)) ABM_LAUNCH(M_INFECT | M_STEP | M_DENSE_I | M_DENSE_A | M_INCR);   // day
     else if (m == (M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A)) ABM_LAUNCH(M_INFECT | M_STEP | M_GO_OUT | M_DENSE_A);
@@ -414,8 +419,8 @@ int abm_create(const abm_config* cfg, abm_handle** out) {
     }
     const size_t pa = (size_t)cfg->n_pools * cfg->n_status;
     int rc;
-    // replicas of the accumulators: a power of two <= 64 keeping each table buffer under 8 MiB
-    h->replicas = 64;
+    // replicas of the accumulators: a power of two <= ABM_MAX_REPLICAS keeping each table buffer under 8 MiB
+    h->replicas = ABM_MAX_REPLICAS;
     while (h->replicas > 1 && (size_t)h->replicas * 2 * pa * sizeof(unsigned long long) > (8u << 20)) h->replicas >>= 1;
     if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[0]))) return rc;
     if ((rc = alloc_zero(h, (size_t)h->replicas * 2 * pa, &h->acc[1]))) return rc;

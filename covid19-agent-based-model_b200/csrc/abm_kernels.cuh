@@ -117,6 +117,9 @@ __device__ __forceinline__ Cold load_cold(const DevAgents& G, uint32_t slot) {
 // blockIdx & rep_mask): atomics on one address serialise in L2, and the hottest rows (the capital's
 // pool, the event tallies) would otherwise receive tens of thousands of them per launch.  The table
 // kernel sums the replicas.
+#ifndef ABM_MAX_REPLICAS
+#define ABM_MAX_REPLICAS 16      // 64 in the first builds: 16 costs the sweeps nothing and the table kernel reads a quarter (-1.4 us per sub-step, profiles/r02c_variants_*.txt)
+#endif
 struct DevWork {
     unsigned long long* acc2[2];    // [replicas][2][P][A] each: R fixed-point sums, then head counts; sub-step k uses acc2[k & 1]
     uint32_t* thr_out;              // [P][A] thresholds from the previous sub-step
@@ -560,7 +563,17 @@ __device__ __forceinline__ uint32_t od_destination(const uint32_t* __restrict__ 
 // All table sums are integers, every draw is keyed by (agent, sub-step, site), so splitting the agents between the two
 // kernels cannot change a result.
 constexpr uint32_t RUNTIME_MODE = 0xFFFFFFFFu;
-constexpr int EVENT_THREADS = 256;        // x 8 CTAs per SM at 32 registers: <= 1024 queues, all resident, one round on a busy night
+// Event kernel shape: 128 threads x 8 CTAs per SM = 64 registers per thread, no spills, and all of the <= 1024 queues
+// resident in one wave (1184 CTA slots).  The 32-register shape of the first split (256 x 8) spilled 236 bytes per thread;
+// its local-memory traffic (3.7 M sectors at 08:00) cost 14 % of the kernel at the peak, 4.6 % of a simulated day
+// (profiles/r02b_variants_*.txt: 256 x 4 at 64 registers is as fast at the peak and slower on quiet nights).
+#ifndef ABM_EVENT_THREADS
+#define ABM_EVENT_THREADS 128
+#endif
+#ifndef ABM_EVENT_MIN_BLOCKS
+#define ABM_EVENT_MIN_BLOCKS (1024 / ABM_EVENT_THREADS)
+#endif
+constexpr int EVENT_THREADS = ABM_EVENT_THREADS;
 constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mover, leaves the district"; low 31 bits = the OD draw
 
 // Funnel loop (rare, irregular locations only): iterate a body over the agents whose bit is set in the per-lane `mask`.
@@ -580,6 +593,9 @@ constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mo
 // queue group.  Entry = (slot | newly-infected << 31, flags, aux, 0): the hot words travel with the entry, so the event
 // kernel reads its queue coalesced and touches only the agent's cold sector.  One atomic per LANE that has anything to
 // append (few lanes do; the queues spread the atomics over up to 1024 addresses).
+#ifndef ABM_PUSH_PREFETCH
+#define ABM_PUSH_PREFETCH 15     // bit 0 / 1: cold sector / hot words of a generic event; bit 2 / 3: the same for a decided leaver
+#endif
 #define ABM_PUSH_EVENTS(ev, newly, lvm, XO)                                                          \
     if (ev) {                                                                                        \
         const uint32_t q = cta & Wk.q_mask;                                                          \
@@ -593,9 +609,9 @@ constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mo
                 const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));    /* untouched */ \
                 const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                \
                 *dst++ = make_uint4((slot0 + j) | ((((newly) >> j) & 1u) << 31), fj, aj, 0u);        \
-                prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS);                     \
-                prefetch_l2_keep(G.flags + slot0 + j);                                               \
-                prefetch_l2_keep(G.aux + slot0 + j);                                                 \
+                if (ABM_PUSH_PREFETCH & 1) prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS); \
+                if (ABM_PUSH_PREFETCH & 2) prefetch_l2_keep(G.flags + slot0 + j);                    \
+                if (ABM_PUSH_PREFETCH & 2) prefetch_l2_keep(G.aux + slot0 + j);                      \
             } while (m);                                                                             \
         }                                                                                            \
         m = (ev) & (lvm);                           /* decided leavers: from the back */             \
@@ -607,9 +623,9 @@ constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mo
                 const uint32_t fj = j == 0 ? f0 : (j == 1 ? f1 : (j == 2 ? f2 : f3));                \
                 const uint32_t aj = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));                \
                 *dst-- = make_uint4(slot0 + j, fj, aj, EV_LEAVER | (word_of(XO, (int)j) >> 1));      \
-                if ((fj & F_EPI_MASK) != EPI_S) prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS); \
-                prefetch_l2_keep(G.flags + slot0 + j);                                               \
-                prefetch_l2_keep(G.aux + slot0 + j);                                                 \
+                if ((ABM_PUSH_PREFETCH & 4) && (fj & F_EPI_MASK) != EPI_S) prefetch_l2_keep(G.cold + (size_t)(slot0 + j) * ABM_COLD_WORDS); \
+                if (ABM_PUSH_PREFETCH & 8) prefetch_l2_keep(G.flags + slot0 + j);                    \
+                if (ABM_PUSH_PREFETCH & 8) prefetch_l2_keep(G.aux + slot0 + j);                      \
             } while (m);                                                                             \
         }                                                                                            \
     }
@@ -618,9 +634,18 @@ constexpr uint32_t EV_LEAVER = 1u << 31;  // entry word 3: the sweep decided "mo
 // sweeps, 5 (48 registers) for the movement sweeps
 // (measured: 6 instead of 8 CTAs on the night sweeps, and 4 or 6 instead of 5 on the movement sweeps, change nothing
 // beyond noise)
-constexpr int sweep_min_blocks(uint32_t mode) { return (mode != RUNTIME_MODE && (mode & M_INCR)) ? 2048 / THREADS : 1280 / THREADS; }
+#ifndef ABM_SWEEP_CTAS_INCR
+#define ABM_SWEEP_CTAS_INCR (2048 / THREADS)
+#endif
+#ifndef ABM_SWEEP_CTAS_MOVE
+#define ABM_SWEEP_CTAS_MOVE (1280 / THREADS)
+#endif
+constexpr int sweep_min_blocks(uint32_t mode) { return (mode != RUNTIME_MODE && (mode & M_INCR)) ? ABM_SWEEP_CTAS_INCR : ABM_SWEEP_CTAS_MOVE; }
 
-template <uint32_t MODE>
+// TRACE: the timeline stamps of abm_set_trace are compiled in only for the instantiation that is launched while a trace
+// buffer is attached.  In the production instantiation they cost the night sweep 24 instructions per warp and, at its
+// 32-register budget, two spilled registers: 3.7 % of the mean sweep launch (profiles/r02b_variants_*.txt).
+template <uint32_t MODE, bool TRACE>
 __global__ void __launch_bounds__(THREADS, sweep_min_blocks(MODE))
 abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* clk, const uint32_t mode_rt) {
     __shared__ uint32_t s_hz[WARPS][SUB];             // per-warp household hazard sums, then thresholds
@@ -628,7 +653,7 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
 
     const uint32_t mode_static = MODE == RUNTIME_MODE ? (mode_rt & 0xFFFFu) : MODE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;
+    const unsigned long long t_start = TRACE ? global_timer_ns() : 0ull;
     // The event kernel may be scheduled as soon as SM resources free up (i.e. while this grid drains): it waits for
     // this grid's completion before it touches anything.
     launch_dependents();
@@ -953,7 +978,7 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
 
     // ================================================================ hand the deferred agents to the event kernel
     ABM_PUSH_EVENTS(defer, newly, leaver, XO)
-    trace_stamp(Wk, s.k, 0, t_start);
+    if (TRACE) trace_stamp(Wk, s.k, 0, t_start);
 
     // ================================================================ flush of the warp's home-pool accumulators
     if ((mode & M_DENSE_A) && !(mode & M_INCR)) {
@@ -977,7 +1002,7 @@ abm_sweep_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const D
 // (update_agent_states + contagious promotion, :226-272, :54-58), go_home / go_out incl. the return from and the
 // departure on a trip (:274-441), and its contribution to the district x status tables.  The hot words come with the
 // queue entry (coalesced); the only scattered accesses are the agent's 32-byte cold sector and the final stores.
-__global__ void __launch_bounds__(EVENT_THREADS, 2048 / EVENT_THREADS)
+__global__ void __launch_bounds__(EVENT_THREADS, ABM_EVENT_MIN_BLOCKS)
 abm_event_kernel(const DevTables T, const DevAgents G, const DevWork Wk, const DevClock* clk, const uint32_t mode_rt) {
     __shared__ int s_tally[N_TALLY];
     const unsigned long long t_start = Wk.trace ? global_timer_ns() : 0ull;

@@ -57,7 +57,7 @@ def main():
     cubin = sorted(f for f in os.listdir(tmp) if f.endswith('.cubin'))[0]
     text = subprocess.run([os.path.join(CUDA_BIN, 'nvdisasm'), '-g', '-c', os.path.join(tmp, cubin)], check=True,
                           capture_output=True, text=True).stdout
-    want = f'abm_sweep_kernelILj{mode}E'
+    want = f'abm_sweep_kernelILj{mode}ELb0E'        # the instantiation without the timeline stamps
     marks = phase_marks(SRC)
 
     def phase_of(line_no):
