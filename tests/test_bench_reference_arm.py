@@ -41,3 +41,14 @@ def test_unmodified_reference_replica_runs():
     ref_file = '/root/reference/src/covid19_abm/base_model.py'
     if os.path.exists(ref_file):
         assert open(ref_file, 'rb').read() == open(os.path.join(ROOT, 'baseline', '_ref', 'src', 'covid19_abm', 'base_model.py'), 'rb').read()
+
+
+def test_clock_sampler_windows():
+    """The SM-clock summary of the bench line: median over the timed region plus the profiled days, first range counted."""
+    import bench
+    c = bench.ClockSampler(0)
+    c.samples, c.max_mhz = [1200, 1965, 1965, 300, 1965, 1950], 1965
+    s = c.summary([(1, 3), (4, 6)])
+    assert s['sm_mhz'] == 1965.0 and s['samples'] == 4 and s['samples_in_timed_region'] == 2 and s['sm_max_mhz'] == 1965.0
+    assert c.summary()['samples'] == 6 and 'window' not in c.summary()
+    assert bench.ClockSampler(0).summary([(0, 0), (0, 0)])['sm_mhz'] is None
