@@ -10,7 +10,7 @@ tail -5 gpurun_out/pytest_$tag.log
 timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -2 gpurun_out/bench_$tag.err
 timeout 300 python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/plain_$tag.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none \
-    -k regex:abm_ -s 480 -c 12 --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/ncu_$tag.log 2>&1
+    -k regex:abm_ -s 720 -c 18 --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/ncu_$tag.log 2>&1
 if [ "$2" == "full" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:abm_sweep -s 240 -c 6 -o gpurun_out/prof_$tag \
       python tools/profile_case.py --spinup 40 --days 2 > gpurun_out/ncu2_$tag.log 2>&1
